@@ -1,0 +1,382 @@
+// rpool_api.cu -- extern "C" entry points of librpool_b200.so (see
+// include/rpool_b200.h for the contract and the reference lines each replaces).
+// Host side only validates, fills kernel parameter blocks and launches; it
+// never allocates device memory and never synchronises (except rpool_read_plan).
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "rpool_kernels.cuh"
+
+using namespace rpool;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+// tuning knobs (process-wide; experiments only)
+std::atomic<int> g_smem_bytes{74 * 1024};
+std::atomic<int> g_threads{256};
+std::atomic<int> g_order{1};
+std::atomic<int> g_force_path{kPathAuto};
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(RPOOL_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CUDA_TRY(expr, what)                              \
+    do {                                                  \
+        cudaError_t e__ = (expr);                         \
+        if (e__ != cudaSuccess) return cuda_fail(e__, what); \
+    } while (0)
+
+// workspace layout: [levels R][order R][keys R] int32
+struct Workspace {
+    int *levels, *order, *keys;
+};
+size_t ws_bytes(int R)
+{
+    const size_t r = ((size_t)(R > 0 ? R : 1) + 31) & ~(size_t)31;
+    return 3 * r * sizeof(int);
+}
+Workspace ws_split(void *ws, int R)
+{
+    const size_t r = ((size_t)(R > 0 ? R : 1) + 31) & ~(size_t)31;
+    Workspace w;
+    w.levels = static_cast<int *>(ws);
+    w.order = w.levels + r;
+    w.keys = w.order + r;
+    return w;
+}
+
+int validate(const rpool_problem *p, void *ws, size_t ws_size, bool need_pooled)
+{
+    if (!p) return fail(RPOOL_ERR_INVALID, "problem is NULL");
+    if (p->n_levels < 1 || p->n_levels > RPOOL_MAX_LEVELS)
+        return fail(RPOOL_ERR_INVALID, "n_levels=%d outside [1,%d]", p->n_levels, RPOOL_MAX_LEVELS);
+    if (p->channels < 1) return fail(RPOOL_ERR_INVALID, "channels=%d", p->channels);
+    if (p->feat_layout != RPOOL_NHWC && p->feat_layout != RPOOL_NCHW)
+        return fail(RPOOL_ERR_INVALID, "feat_layout=%d", p->feat_layout);
+    if (p->pool_layout != RPOOL_NHWC && p->pool_layout != RPOOL_NCHW)
+        return fail(RPOOL_ERR_INVALID, "pool_layout=%d", p->pool_layout);
+    if (p->roi_format != RPOOL_ROI_XY && p->roi_format != RPOOL_ROI_YX)
+        return fail(RPOOL_ERR_INVALID, "roi_format=%d", p->roi_format);
+    if (p->n_rois < 0) return fail(RPOOL_ERR_INVALID, "n_rois=%d", p->n_rois);
+    if (p->n_rois > 0 && !p->rois) return fail(RPOOL_ERR_INVALID, "rois is NULL");
+    for (int l = 0; l < p->n_levels; ++l) {
+        const rpool_level &L = p->level[l];
+        if (!L.data || L.n_images < 1 || L.height < 1 || L.width < 1)
+            return fail(RPOOL_ERR_INVALID, "level %d: data=%p n=%d h=%d w=%d", l, L.data,
+                        L.n_images, L.height, L.width);
+        if ((double)L.n_images * L.height * L.width * p->channels >= 2147483648.0 * 4)
+            return fail(RPOOL_ERR_UNSUPPORTED, "level %d has more than 2^33 elements", l);
+        if ((double)L.height * L.width * p->channels >= 2147483648.0)
+            return fail(RPOOL_ERR_UNSUPPORTED, "level %d: one image exceeds 2^31 elements", l);
+    }
+    if (p->n_heads < 1 || p->n_heads > RPOOL_MAX_HEADS)
+        return fail(RPOOL_ERR_INVALID, "n_heads=%d outside [1,%d]", p->n_heads, RPOOL_MAX_HEADS);
+    for (int h = 0; h < p->n_heads; ++h) {
+        if (p->out_h[h] < 1 || p->out_w[h] < 1)
+            return fail(RPOOL_ERR_INVALID, "head %d: out %dx%d", h, p->out_h[h], p->out_w[h]);
+        if (need_pooled && p->n_rois > 0 && !p->pooled[h])
+            return fail(RPOOL_ERR_INVALID, "head %d: pooled pointer is NULL", h);
+        if ((double)p->out_h[h] * p->out_w[h] * p->channels >= 2147483648.0)
+            return fail(RPOOL_ERR_UNSUPPORTED, "head %d: one pooled RoI exceeds 2^31 elements", h);
+    }
+    if (p->coord_mode != RPOOL_COORD_CHAINER && p->coord_mode != RPOOL_COORD_CAFFE2)
+        return fail(RPOOL_ERR_INVALID, "coord_mode=%d", p->coord_mode);
+    if (p->coord_mode == RPOOL_COORD_CHAINER && p->sampling_ratio != 1)
+        return fail(RPOOL_ERR_INVALID,
+                    "RPOOL_COORD_CHAINER samples once per bin: sampling_ratio must be 1, got %d",
+                    p->sampling_ratio);
+    if (p->sampling_ratio > 64)
+        return fail(RPOOL_ERR_UNSUPPORTED, "sampling_ratio=%d > 64", p->sampling_ratio);
+    if (!p->roi_levels && !p->roi_levels_f32 && p->n_levels > 1) {
+        if (p->n_thresholds < 0 || p->n_thresholds > RPOOL_MAX_LEVELS)
+            return fail(RPOOL_ERR_INVALID, "n_thresholds=%d", p->n_thresholds);
+    }
+    if (!ws) return fail(RPOOL_ERR_WORKSPACE, "workspace is NULL");
+    if (ws_size < ws_bytes(p->n_rois))
+        return fail(RPOOL_ERR_WORKSPACE, "workspace has %zu bytes, %zu needed", ws_size,
+                    ws_bytes(p->n_rois));
+    return RPOOL_OK;
+}
+
+int fill_params(const rpool_problem *p, const Workspace &w, KParams &k)
+{
+    memset(&k, 0, sizeof(k));
+    for (int l = 0; l < p->n_levels; ++l) {
+        k.lvl[l].data = static_cast<float *>(p->level[l].data);
+        k.lvl[l].n_images = p->level[l].n_images;
+        k.lvl[l].H = p->level[l].height;
+        k.lvl[l].W = p->level[l].width;
+        k.lvl[l].scale = p->level[l].spatial_scale;
+    }
+    k.n_levels = p->n_levels;
+    k.C = p->channels;
+    k.feat_layout = p->feat_layout;
+    k.pool_layout = p->pool_layout;
+    k.rois = p->rois;
+    k.R = p->n_rois;
+    k.roi_format = p->roi_format;
+    k.roi_level = w.levels;
+    k.order = w.order;
+    k.n_heads = p->n_heads;
+    for (int h = 0; h < p->n_heads; ++h) {
+        k.PH[h] = p->out_h[h];
+        k.PW[h] = p->out_w[h];
+        k.pooled[h] = static_cast<float *>(p->pooled[h]);
+    }
+    k.S = p->sampling_ratio;
+    k.mode = p->coord_mode;
+    k.force_path = g_force_path.load();
+    const int ctl = (int)((sizeof(BlockCtl) + 127) & ~(size_t)127);
+    int smem = g_smem_bytes.load();
+    if (smem < ctl + 1024) smem = ctl + 1024;
+    k.win_floats = (smem - ctl) / 4;
+    return smem;
+}
+
+template <typename Kern>
+int set_smem(Kern kern, int smem)
+{
+    // Raising the dynamic shared memory limit is per device and cheap; do it
+    // on every launch so that multi-device processes need no bookkeeping.
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+             "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    return RPOOL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rpool_version(void) { return RPOOL_VERSION; }
+
+const char *rpool_last_error(void) { return g_err; }
+
+uint64_t rpool_launch_count(void) { return g_launches.load(); }
+
+int rpool_set_tuning(const char *key, int value)
+{
+    if (!key) return fail(RPOOL_ERR_INVALID, "key is NULL");
+    if (!strcmp(key, "smem_bytes")) {
+        if (value < 8 * 1024 || value > 227 * 1024)
+            return fail(RPOOL_ERR_INVALID, "smem_bytes=%d outside [8K,227K]", value);
+        g_smem_bytes = value;
+    } else if (!strcmp(key, "threads")) {
+        if (value < 32 || value > 512 || value % 32)
+            return fail(RPOOL_ERR_INVALID, "threads=%d must be a multiple of 32 in [32,512]", value);
+        g_threads = value;
+    } else if (!strcmp(key, "order")) {
+        if (value < 0 || value > 2) return fail(RPOOL_ERR_INVALID, "order=%d outside [0,2]", value);
+        g_order = value;
+    } else if (!strcmp(key, "force_path")) {
+        if (value < 0 || value > 3) return fail(RPOOL_ERR_INVALID, "force_path=%d outside [0,3]", value);
+        g_force_path = value;
+    } else {
+        return fail(RPOOL_ERR_INVALID, "unknown tuning key '%s'", key);
+    }
+    return RPOOL_OK;
+}
+
+int rpool_get_tuning(const char *key, int *value)
+{
+    if (!key || !value) return fail(RPOOL_ERR_INVALID, "NULL argument");
+    if (!strcmp(key, "smem_bytes")) *value = g_smem_bytes;
+    else if (!strcmp(key, "threads")) *value = g_threads;
+    else if (!strcmp(key, "order")) *value = g_order;
+    else if (!strcmp(key, "force_path")) *value = g_force_path;
+    else return fail(RPOOL_ERR_INVALID, "unknown tuning key '%s'", key);
+    return RPOOL_OK;
+}
+
+int rpool_level_thresholds(float s0, float lvl0, float eps, int k_min, int k_max, float *out)
+{
+    if (!out || k_max < k_min) return fail(RPOOL_ERR_INVALID, "bad arguments");
+    auto level_of = [&](float area) -> float {
+        // float32 pipeline of multilevel_region_proposal_network.py:24-30
+        volatile float s = sqrtf(area);
+        volatile float q = s / s0;
+        volatile float a = q + eps;
+        volatile float lg = log2f(a);
+        volatile float t = lvl0 + lg;
+        return floorf(t);
+    };
+    for (int k = k_min + 1; k <= k_max; ++k) {
+        uint32_t lo = 0u;           // level(lo) < k
+        uint32_t hi = 0x7f000000u;  // level(hi) >= k  (1.7e38)
+        float fhi;
+        memcpy(&fhi, &hi, 4);
+        if (!(level_of(fhi) >= (float)k))
+            return fail(RPOOL_ERR_INVALID, "level %d is unreachable", k);
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            float fm;
+            memcpy(&fm, &mid, 4);
+            if (level_of(fm) >= (float)k) hi = mid; else lo = mid;
+        }
+        memcpy(&out[k - k_min - 1], &hi, 4);
+    }
+    return RPOOL_OK;
+}
+
+int rpool_assign_levels(const float *boxes, int32_t n, int32_t box_stride, int32_t roi_format,
+                        const float *thr, int32_t n_thr, int32_t k_min, int32_t k_cap,
+                        float *levels_f32, int32_t *levels_i32, void *stream)
+{
+    if (n < 0 || (n > 0 && !boxes)) return fail(RPOOL_ERR_INVALID, "boxes");
+    if (box_stride != 4 && box_stride != 5) return fail(RPOOL_ERR_INVALID, "box_stride=%d", box_stride);
+    if (n_thr < 0 || n_thr > RPOOL_MAX_LEVELS || (n_thr > 0 && !thr))
+        return fail(RPOOL_ERR_INVALID, "n_thresholds=%d", n_thr);
+    if (roi_format != RPOOL_ROI_XY && roi_format != RPOOL_ROI_YX)
+        return fail(RPOOL_ERR_INVALID, "roi_format=%d", roi_format);
+    if (n == 0) return RPOOL_OK;
+    LevelParams p;
+    memset(&p, 0, sizeof(p));
+    p.boxes = boxes; p.n = n; p.stride = box_stride; p.roi_format = roi_format;
+    for (int t = 0; t < n_thr; ++t) p.thr[t] = thr[t];
+    p.n_thr = n_thr; p.k_min = k_min; p.k_cap = k_cap;
+    p.out_f = levels_f32; p.out_i = levels_i32;
+    rpool_levels_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    CUDA_TRY(cudaGetLastError(), "rpool_levels_kernel launch");
+    g_launches++;
+    return RPOOL_OK;
+}
+
+size_t rpool_workspace_bytes(int32_t n_rois) { return ws_bytes(n_rois); }
+
+size_t rpool_problem_size(void) { return sizeof(rpool_problem); }
+
+int rpool_plan(const rpool_problem *p, void *ws, size_t ws_size, void *stream)
+{
+    int rc = validate(p, ws, ws_size, false);
+    if (rc) return rc;
+    if (p->n_rois == 0) return RPOOL_OK;
+    const Workspace w = ws_split(ws, p->n_rois);
+    PlanParams k;
+    memset(&k, 0, sizeof(k));
+    k.rois = p->rois; k.R = p->n_rois; k.roi_format = p->roi_format;
+    k.given_levels = p->roi_levels;
+    k.given_levels_f32 = p->roi_levels ? nullptr : p->roi_levels_f32;
+    k.n_thr = (p->roi_levels || p->roi_levels_f32 || p->n_levels == 1) ? 0 : p->n_thresholds;
+    for (int t = 0; t < k.n_thr; ++t) k.thr[t] = p->level_thresholds[t];
+    k.k_min = p->k_min;
+    k.n_levels = p->n_levels;
+    int nimg = 1;
+    for (int l = 0; l < p->n_levels; ++l) nimg = p->level[l].n_images > nimg ? p->level[l].n_images : nimg;
+    k.n_images = nimg;
+    k.order_mode = g_order.load();
+    k.levels = w.levels; k.order = w.order; k.keys = w.keys;
+    rpool_plan_kernel<<<1, kPlanThreads, 0, static_cast<cudaStream_t>(stream)>>>(k);
+    CUDA_TRY(cudaGetLastError(), "rpool_plan_kernel launch");
+    g_launches++;
+    return RPOOL_OK;
+}
+
+int rpool_forward(const rpool_problem *p, void *ws, size_t ws_size, void *stream)
+{
+    int rc = validate(p, ws, ws_size, true);
+    if (rc) return rc;
+    if (p->n_rois == 0) return RPOOL_OK;
+    KParams k;
+    const int smem = fill_params(p, ws_split(ws, p->n_rois), k);
+    rc = set_smem(rpool_forward_kernel, smem);
+    if (rc) return rc;
+    rpool_forward_kernel<<<p->n_rois, g_threads.load(), smem, static_cast<cudaStream_t>(stream)>>>(k);
+    CUDA_TRY(cudaGetLastError(), "rpool_forward_kernel launch");
+    g_launches++;
+    return RPOOL_OK;
+}
+
+int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *stream)
+{
+    int rc = validate(p, ws, ws_size, true);
+    if (rc) return rc;
+    if (p->deterministic)
+        return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward is not implemented yet");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!p->accumulate) {
+        ZeroParams z;
+        memset(&z, 0, sizeof(z));
+        z.n = p->n_levels;
+        unsigned long long most = 0;
+        for (int l = 0; l < p->n_levels; ++l) {
+            const unsigned long long n = (unsigned long long)p->level[l].n_images *
+                                         p->level[l].height * p->level[l].width * p->channels;
+            z.ptr[l] = static_cast<float *>(p->level[l].data);
+            if (reinterpret_cast<uintptr_t>(z.ptr[l]) & 15) { z.n4[l] = 0; z.tail[l] = n; }
+            else { z.n4[l] = n / 4; z.tail[l] = n % 4; }
+            most = z.n4[l] > most ? z.n4[l] : most;
+            if (z.tail[l] > 1024ull * 148 * 8)
+                return fail(RPOOL_ERR_UNSUPPORTED, "level %d gradient is not 16-byte aligned", l);
+        }
+        rpool_zero_kernel<<<148 * 8, 1024, 0, st>>>(z);
+        CUDA_TRY(cudaGetLastError(), "rpool_zero_kernel launch");
+        g_launches++;
+    }
+    if (p->n_rois == 0) return RPOOL_OK;
+    KParams k;
+    const int smem = fill_params(p, ws_split(ws, p->n_rois), k);
+    rc = set_smem(rpool_backward_kernel, smem);
+    if (rc) return rc;
+    rpool_backward_kernel<<<p->n_rois, g_threads.load(), smem, st>>>(k);
+    CUDA_TRY(cudaGetLastError(), "rpool_backward_kernel launch");
+    g_launches++;
+    return RPOOL_OK;
+}
+
+int rpool_read_plan(const void *ws, int32_t n_rois, int32_t *levels_host, int32_t *order_host,
+                    void *stream)
+{
+    if (!ws || n_rois < 0) return fail(RPOOL_ERR_INVALID, "bad arguments");
+    const Workspace w = ws_split(const_cast<void *>(ws), n_rois);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (levels_host)
+        CUDA_TRY(cudaMemcpyAsync(levels_host, w.levels, sizeof(int) * n_rois, cudaMemcpyDeviceToHost, st),
+                 "copy levels");
+    if (order_host)
+        CUDA_TRY(cudaMemcpyAsync(order_host, w.order, sizeof(int) * n_rois, cudaMemcpyDeviceToHost, st),
+                 "copy order");
+    CUDA_TRY(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    return RPOOL_OK;
+}
+
+static int transpose(const float *src, float *dst, int n, int rows, int cols, void *stream)
+{
+    if (!src || !dst || n < 1 || rows < 1 || cols < 1) return fail(RPOOL_ERR_INVALID, "bad arguments");
+    if (n > 65535) return fail(RPOOL_ERR_UNSUPPORTED, "more than 65535 images");
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, n), block(32, 8);
+    if (grid.y > 65535) return fail(RPOOL_ERR_UNSUPPORTED, "plane too large");
+    rpool_transpose_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, rows, cols);
+    CUDA_TRY(cudaGetLastError(), "rpool_transpose_kernel launch");
+    g_launches++;
+    return RPOOL_OK;
+}
+
+int rpool_nchw_to_nhwc(const float *src, float *dst, int32_t n, int32_t c, int32_t h, int32_t w,
+                       void *stream)
+{
+    return transpose(src, dst, n, c, h * w, stream);  // (C, HW) -> (HW, C)
+}
+
+int rpool_nhwc_to_nchw(const float *src, float *dst, int32_t n, int32_t c, int32_t h, int32_t w,
+                       void *stream)
+{
+    return transpose(src, dst, n, h * w, c, stream);  // (HW, C) -> (C, HW)
+}
+
+}  // extern "C"

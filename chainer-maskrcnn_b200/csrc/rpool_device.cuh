@@ -1,0 +1,310 @@
+// rpool_device.cuh -- device-side building blocks of the fused multi-level
+// RoIAlign kernels (sm_100a).  Geometry follows, operation for operation, the
+// reference's two coordinate recipes so that sample coordinates are bit-equal
+// to the reference's (a 1-ulp difference in a coordinate near 300 is a 3e-5
+// change of the interpolation weight, above the 1e-5 forward tolerance):
+//   RPOOL_COORD_CHAINER: chainer_maskrcnn/functions/roi_align/roi_align_2d.py
+//       forward :56-78, backward :154-178 (as evaluated by NumPy 2.x)
+//   RPOOL_COORD_CAFFE2:  .../caffe2_operation/caffe2_roi_align.cpp:36-94,147-174
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/rpool_b200.h"
+
+namespace rpool {
+
+constexpr int kNT = 4;        // footprint width kept per bin and axis on the fast path
+constexpr int kPMax = 32;     // largest pooled extent served by the fast path
+constexpr int kMaxHeads = RPOOL_MAX_HEADS;
+constexpr int kMaxLevels = RPOOL_MAX_LEVELS;
+
+enum Path : int { kPathAuto = 0, kPathGeneric = 1, kPathDirect = 2, kPathStaged = 3 };
+
+struct LevelDev {
+    float *data;
+    int n_images, H, W;
+    float scale;
+};
+
+struct KParams {
+    LevelDev lvl[kMaxLevels];
+    int n_levels;
+    int C;
+    int feat_layout, pool_layout;
+    const float *rois;
+    int R;
+    int roi_format;
+    const int *roi_level;  // resolved per-RoI level (plan output), never null at launch
+    const int *order;      // launch schedule (plan output)
+    int n_heads;
+    int PH[kMaxHeads], PW[kMaxHeads];
+    float *pooled[kMaxHeads];
+    int S;
+    int mode;
+    int win_floats;  // capacity of the staged window, in floats
+    int force_path;
+};
+
+// ---------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------
+struct AxisGeom {
+    float start;      // RoI origin on the feature map
+    float stride_f;   // chainer: float32 stride; caffe2: bin size
+    double stride_d;  // chainer: double stride where the reference uses Python floats
+    int use_dbl;
+    int grid;         // samples per bin along this axis
+    int size;         // H or W
+    float inv_grid;
+};
+
+__device__ __forceinline__ AxisGeom make_axis(int mode, bool bwd, float lo, float hi,
+                                              float scale, int P, int S, int size)
+{
+    AxisGeom g;
+    g.start = __fmul_rn(lo, scale);
+    const float end = __fmul_rn(hi, scale);
+    const float len = __fsub_rn(end, g.start);
+    g.size = size;
+    g.stride_d = 0.0;
+    g.use_dbl = 0;
+    if (mode == RPOOL_COORD_CHAINER) {
+        // max(len, 1.) is Python's max: keeps len unless 1. > len.
+        const bool clamped = (1.0f > len);
+        if (!bwd) {
+            // stride = 1. * size / out  (float32) -- or a double when the clamp
+            // returned the Python float 1.0                        (:62-65)
+            g.use_dbl = clamped;
+            g.stride_f = __fdiv_rn(len, (float)P);
+            g.stride_d = 1.0 / (double)P;
+        } else {
+            // stride = float(size) / float(out): always a double    (:161-165)
+            g.use_dbl = 1;
+            g.stride_f = 0.f;
+            g.stride_d = (clamped ? 1.0 : (double)len) / (double)P;
+        }
+        g.grid = 1;
+    } else {
+        const float l = (len < 1.0f) ? 1.0f : len;  // std::max(len, 1)  (:162-163)
+        g.stride_f = __fdiv_rn(l, (float)P);         // bin size          (:164-165)
+        g.grid = (S > 0) ? S : (int)ceilf(g.stride_f);  // roi_bin_grid    (:167-171)
+    }
+    g.inv_grid = 1.0f / (float)(g.grid > 0 ? g.grid : 1);
+    return g;
+}
+
+// One sample along one axis: the two taps (i0 <= i1), their weights, and
+// whether the sample counts at all (caffe2 drops samples beyond [-1, size]).
+__device__ __forceinline__ bool axis_sample(const AxisGeom &g, int mode, int p, int s,
+                                            int &i0, int &i1, float &w0, float &w1)
+{
+    const int bound = g.size - 1;
+    if (mode == RPOOL_COORD_CHAINER) {
+        float c;
+        if (g.use_dbl)
+            c = __fadd_rn((float)(((double)p + 0.5) * g.stride_d), g.start);
+        else
+            c = __fadd_rn(__fmul_rn((float)p + 0.5f, g.stride_f), g.start);
+        const float fl = floorf(c);
+        const float fr = __fsub_rn(c, fl);
+        int lo = (int)fl;
+        lo = lo < 0 ? 0 : lo;          // numpy.maximum(floor, 0)
+        lo = lo > bound ? bound : lo;  // safety only: the reference raises IndexError here
+        int hi = lo + 1;
+        hi = hi > bound ? bound : hi;  // numpy.minimum(x0 + 1, size - 1)
+        i0 = lo;
+        i1 = hi;
+        w1 = fr;
+        w0 = __fsub_rn(1.0f, fr);
+        return true;
+    } else {
+        // start + p*bin + (s + .5)*bin/grid, left to right, each op rounded
+        float c = __fadd_rn(__fadd_rn(g.start, __fmul_rn((float)p, g.stride_f)),
+                            __fdiv_rn(__fmul_rn((float)s + 0.5f, g.stride_f), (float)g.grid));
+        const bool valid = !(c < -1.0f || c > (float)g.size);
+        if (c <= 0.f) c = 0.f;
+        int lo = (int)c, hi;
+        if (lo >= bound) {
+            hi = lo = bound;
+            c = (float)lo;
+        } else {
+            hi = lo + 1;
+        }
+        const float l = __fsub_rn(c, (float)lo);
+        i0 = lo;
+        i1 = hi;
+        w1 = l;
+        w0 = __fsub_rn(1.0f, l);
+        return valid;
+    }
+}
+
+struct RoiBox {
+    int b;
+    float x1, y1, x2, y2;
+};
+
+__device__ __forceinline__ RoiBox load_roi(const float *rois, int r, int roi_format)
+{
+    const float *p = rois + (size_t)r * 5;
+    RoiBox q;
+    q.b = (int)__ldg(p);
+    const float a = __ldg(p + 1), b = __ldg(p + 2), c = __ldg(p + 3), d = __ldg(p + 4);
+    if (roi_format == RPOOL_ROI_YX) {
+        q.y1 = a; q.x1 = b; q.y2 = c; q.x2 = d;
+    } else {
+        q.x1 = a; q.y1 = b; q.x2 = c; q.y2 = d;
+    }
+    return q;
+}
+
+// ---------------------------------------------------------------------------
+// per-RoI footprint tables (fast path)
+// ---------------------------------------------------------------------------
+// For bin p of one axis the S samples' 2S taps are merged into a dense run of
+// at most kNT cells starting at lo[p]; w[p] holds the summed weights (already
+// divided by the grid size).  lo[] is non-decreasing in p.
+struct AxisTab {
+    int lo[kPMax];
+    int n[kPMax];
+    float4 w[kPMax];
+};
+
+struct BlockCtl {
+    AxisTab tab[kMaxHeads][2];  // [head][0 = y, 1 = x]
+    int wmin[2], wmax[2];       // window extent over all heads: [0] rows, [1] cols
+    int eligible;
+    int pad_;
+    unsigned long long mbar;
+};
+
+// Fills entry p of `t`; returns false when the footprint does not fit kNT cells.
+__device__ __forceinline__ bool fill_axis_entry(AxisTab &t, const AxisGeom &g, int mode, int p,
+                                                int &lo_out, int &hi_out)
+{
+    float w[kNT] = {0.f, 0.f, 0.f, 0.f};
+    int lo = 0, n = 0;
+    bool ok = true;
+    for (int s = 0; s < g.grid; ++s) {
+        int i0, i1;
+        float w0, w1;
+        const bool valid = axis_sample(g, mode, p, s, i0, i1, w0, w1);
+        if (s == 0) lo = i0;
+        if (!valid) continue;
+        const int o0 = i0 - lo, o1 = i1 - lo;
+        if (o1 >= kNT || o0 < 0) {
+            ok = false;
+            break;
+        }
+#pragma unroll
+        for (int k = 0; k < kNT; ++k) {
+            if (k == o0) w[k] += w0 * g.inv_grid;
+            if (k == o1) w[k] += w1 * g.inv_grid;
+        }
+        n = o1 + 1 > n ? o1 + 1 : n;
+    }
+    if (g.grid > kNT) ok = false;
+    t.lo[p] = lo;
+    t.n[p] = n;
+    t.w[p] = make_float4(w[0], w[1], w[2], w[3]);
+    lo_out = lo;
+    hi_out = lo + n - 1;
+    return ok;
+}
+
+// ---------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ float4 lds128(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v)
+{
+    asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory");
+}
+// streaming (evict-first) global accesses for data touched exactly once
+__device__ __forceinline__ void stg_stream128(float *p, float4 v)
+{
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float ldg_stream32(const float *p)
+{
+    float v;
+    asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_nc128(const float *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+// vector float reduction to global memory (sm_90+): one L2 atomic per 16 bytes
+__device__ __forceinline__ void red_add_v4(float *p, float4 v)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float *p, float v)
+{
+    asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+
+// mbarrier + bulk async copy (the non-tensor TMA path: UBLKCP in SASS)
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    const uint32_t a = smem_u32(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, unsigned bytes,
+                                         unsigned long long *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+}  // namespace rpool

@@ -1,0 +1,195 @@
+/*
+ * rpool_b200.h -- C ABI of the B200-native FPN multi-level RoIAlign library
+ * (librpool_b200.so, built from chainer-maskrcnn_b200/csrc/ for sm_100a).
+ *
+ * This is the drop-in boundary for the reference's RoI feature-pooling path.
+ * Citations are relative to the katotetsuro/chainer-maskrcnn tree:
+ *
+ *   rpool_forward / rpool_backward replace
+ *     - the CuPy kernels roi_align_2d_fwd / roi_align_2d_bwd
+ *       (chainer_maskrcnn/functions/roi_align/roi_align_2d.py:100-144, :196-279),
+ *     - the pybind11 module caffe2_roi_align.forward
+ *       (.../caffe2_operation/caffe2_roi_align.cpp:231-248), and
+ *     - the heads' per-RoI dispatch loops that call them once per RoI
+ *       (chainer_maskrcnn/model/head/fpn_roi_mask_head.py:57-63,74-78,90-95;
+ *        fpn_roi_keypoint_head.py:59-71,83-87,99-104)
+ *     with ONE launch per direction over the whole pyramid and all heads.
+ *   rpool_assign_levels replaces map_rois_to_fpn_levels
+ *       (chainer_maskrcnn/model/rpn/multilevel_region_proposal_network.py:16-31)
+ *       plus the clip at chainer_maskrcnn/model/maskrcnn.py:141.
+ *   roi_format RPOOL_ROI_YX folds in _roi_align_2d_yx's column permutation
+ *       (chainer_maskrcnn/functions/roi_align_2d_yx.py:5).
+ *
+ * Conventions
+ *   - plain C: raw device pointers, sizes, a POD problem descriptor; no
+ *     allocation inside the library (caller owns outputs and workspace);
+ *   - every entry point that launches work takes a cudaStream_t passed as
+ *     void* and is asynchronous: no hidden device synchronisation;
+ *   - return value 0 = RPOOL_OK, otherwise an rpool_status; the message of the
+ *     last failure on the calling thread is at rpool_last_error();
+ *   - there is no CPU fallback: without a CUDA device every launch fails.
+ */
+#ifndef RPOOL_B200_H_
+#define RPOOL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPOOL_VERSION 100          /* 0.1.0 */
+#define RPOOL_MAX_LEVELS 8
+#define RPOOL_MAX_HEADS 2
+
+#if defined(__GNUC__)
+#define RPOOL_API __attribute__((visibility("default")))
+#else
+#define RPOOL_API
+#endif
+
+typedef enum rpool_status {
+    RPOOL_OK = 0,
+    RPOOL_ERR_INVALID = 1,      /* bad argument (null pointer, size, enum)       */
+    RPOOL_ERR_UNSUPPORTED = 2,  /* valid but not implemented combination         */
+    RPOOL_ERR_WORKSPACE = 3,    /* workspace missing or too small                */
+    RPOOL_ERR_CUDA = 4          /* a CUDA runtime call failed (see last_error)   */
+} rpool_status;
+
+typedef enum rpool_layout {
+    RPOOL_NHWC = 0,  /* channels-last: features (N,H,W,C), pooled (R,PH,PW,C)    */
+    RPOOL_NCHW = 1   /* the reference's layout: (N,C,H,W), (R,C,PH,PW)           */
+} rpool_layout;
+
+typedef enum rpool_roi_format {
+    RPOOL_ROI_XY = 0,  /* [batch, x1, y1, x2, y2]  roi_align_2d.py:296-297        */
+    RPOOL_ROI_YX = 1   /* [batch, y1, x1, y2, x2]  the heads' indices_and_rois    */
+} rpool_roi_format;
+
+typedef enum rpool_coord_mode {
+    /* reference NumPy path: one sample at the bin centre, forward and backward
+     * coordinates rounded exactly as roi_align_2d.py:56-78 / :154-178 do under
+     * NumPy 2.x.  Requires sampling_ratio == 1. */
+    RPOOL_COORD_CHAINER = 0,
+    /* caffe2 semantics of the reference C++ port (caffe2_roi_align.cpp:19-113):
+     * sampling_ratio x sampling_ratio samples per bin (<=0: adaptive grid),
+     * samples beyond [-1, size] contribute zero; backward is its adjoint. */
+    RPOOL_COORD_CAFFE2 = 1
+} rpool_coord_mode;
+
+/* One pyramid level.  `data` is the feature map in rpool_forward (read) and
+ * the dense feature gradient in rpool_backward (written). */
+typedef struct rpool_level {
+    void *data;
+    int32_t n_images;
+    int32_t height;
+    int32_t width;
+    float spatial_scale; /* 1/stride, feature_pyramid_network.py:9-11 */
+} rpool_level;
+
+typedef struct rpool_problem {
+    /* pyramid */
+    int32_t n_levels;   /* 1 = the single-level op roi_align_2d                  */
+    int32_t channels;
+    int32_t feat_layout; /* rpool_layout of every level                           */
+    int32_t pool_layout; /* rpool_layout of pooled outputs / their gradients      */
+    rpool_level level[RPOOL_MAX_LEVELS];
+
+    /* RoIs: device pointer to (n_rois, 5) float32 */
+    const float *rois;
+    int32_t n_rois;
+    int32_t roi_format; /* rpool_roi_format */
+
+    /* Level of each RoI: device int32[n_rois] (clipped to the pyramid like
+     * maskrcnn.py:141), or NULL to assign on the device from the area
+     * thresholds below (level = k_min + #{t : thresholds[t] <= area}). */
+    const int32_t *roi_levels;
+    /* Same, as the float32 array map_rois_to_fpn_levels returns (the heads cast
+     * it with astype(int32), fpn_roi_mask_head.py:58).  Used when roi_levels is
+     * NULL and this is not. */
+    const float *roi_levels_f32;
+    float level_thresholds[RPOOL_MAX_LEVELS];
+    int32_t n_thresholds;
+    int32_t k_min;
+
+    /* heads pooled in the same launch (box 7x7, mask 14x14 ...) */
+    int32_t n_heads;
+    int32_t out_h[RPOOL_MAX_HEADS];
+    int32_t out_w[RPOOL_MAX_HEADS];
+    /* forward: outputs (written).  backward: upstream gradients gy (read). */
+    void *pooled[RPOOL_MAX_HEADS];
+
+    int32_t sampling_ratio;
+    int32_t coord_mode; /* rpool_coord_mode */
+
+    /* backward only */
+    int32_t accumulate;    /* 0: gradients are zero-filled first; 1: += into them */
+    int32_t deterministic; /* 0: atomics; 1: run-to-run reproducible summation     */
+} rpool_problem;
+
+RPOOL_API int rpool_version(void);
+RPOOL_API const char *rpool_last_error(void);
+
+/* Number of kernels this library has launched in the calling process. */
+RPOOL_API uint64_t rpool_launch_count(void);
+
+/* Tuning knobs for experiments ("smem_bytes", "threads", "order", "force_path").
+ * Unknown keys return RPOOL_ERR_INVALID. */
+RPOOL_API int rpool_set_tuning(const char *key, int value);
+RPOOL_API int rpool_get_tuning(const char *key, int *value);
+
+/* Host helper: float32 area thresholds of floor(lvl0 + log2(sqrt(area)/s0 + eps))
+ * for levels k_min+1..k_max, found by bisection with this libc's log2f.  The
+ * Python shim derives them from NumPy instead (the reference's arithmetic) and
+ * the tests assert that both agree.  Writes k_max-k_min floats. */
+RPOOL_API int rpool_level_thresholds(float s0, float lvl0, float eps, int k_min, int k_max,
+                           float *out_thresholds);
+
+/* map_rois_to_fpn_levels on the device.  boxes: (n, box_stride) float32 whose
+ * LAST four columns are the box in `roi_format` order (box_stride 4 or 5).
+ * level = clip(k_min + #{t: thr[t] <= (y2-y1)*(x2-x1)}, k_min, k_cap).
+ * Either output may be NULL. */
+RPOOL_API int rpool_assign_levels(const float *boxes, int32_t n, int32_t box_stride, int32_t roi_format,
+                        const float *thresholds_host, int32_t n_thresholds,
+                        int32_t k_min, int32_t k_cap,
+                        float *levels_f32, int32_t *levels_i32, void *stream);
+
+/* Scratch needed by rpool_plan/forward/backward for up to n_rois RoIs. */
+RPOOL_API size_t rpool_workspace_bytes(int32_t n_rois);
+
+/* sizeof(rpool_problem) as compiled, so that FFI bindings can verify their
+ * struct layout against the library's. */
+RPOOL_API size_t rpool_problem_size(void);
+
+/* Bins the RoIs by (image, level) into the launch schedule kept in `workspace`
+ * (level of every RoI + a stable permutation).  Must precede forward/backward
+ * on the same stream; a plan stays valid while rois/roi_levels are unchanged. */
+RPOOL_API int rpool_plan(const rpool_problem *problem, void *workspace, size_t workspace_bytes,
+               void *stream);
+
+/* pooled[h][r] = RoIAlign(level[lvl(r)].data, rois[r]) for every head h; row r
+ * of every output corresponds to input RoI r (fpn_roi_mask_head.py:59-63). */
+RPOOL_API int rpool_forward(const rpool_problem *problem, void *workspace, size_t workspace_bytes,
+                  void *stream);
+
+/* level[l].data (+)= sum over heads and RoIs of the transposed interpolation
+ * applied to pooled[h] (= gy).  No gradient w.r.t. RoIs (roi_align_2d.py:190). */
+RPOOL_API int rpool_backward(const rpool_problem *problem, void *workspace, size_t workspace_bytes,
+                   void *stream);
+
+/* Read back the schedule of the last plan (for tests): device->host copies of
+ * the per-RoI level and the permutation; synchronises `stream`. */
+RPOOL_API int rpool_read_plan(const void *workspace, int32_t n_rois, int32_t *levels_host,
+                    int32_t *order_host, void *stream);
+
+/* Layout conversion for callers that hold the reference's NCHW arrays. */
+RPOOL_API int rpool_nchw_to_nhwc(const float *src, float *dst, int32_t n, int32_t c, int32_t h,
+                       int32_t w, void *stream);
+RPOOL_API int rpool_nhwc_to_nchw(const float *src, float *dst, int32_t n, int32_t c, int32_t h,
+                       int32_t w, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPOOL_B200_H_ */

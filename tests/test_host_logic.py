@@ -1,0 +1,121 @@
+"""CPU: host-side mirror of the reference interface (names, signatures, type
+checks) and the multi-GPU partitioning, including a world_size-2 gloo run."""
+import inspect
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import chainer_maskrcnn_b200 as pkg
+from chainer_maskrcnn_b200 import _engine, _sharding
+from chainer_maskrcnn_b200.functions.roi_align.roi_align_2d import ROIAlign2D, InvalidType, roi_align_2d
+from chainer_maskrcnn_b200.functions.roi_align_2d_yx import _roi_align_2d_yx
+from chainer_maskrcnn_b200.model.rpn.multilevel_region_proposal_network import map_rois_to_fpn_levels
+from chainer_maskrcnn_b200.model.extractor import feature_pyramid_network as fpn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_names_and_signatures():
+    # roi_align_2d.py:18, :284 ; roi_align_2d_yx.py:4 ; multilevel_region_proposal_network.py:16
+    assert list(inspect.signature(ROIAlign2D.__init__).parameters)[:4] == \
+        ["self", "outh", "outw", "spatial_scale"]
+    assert list(inspect.signature(roi_align_2d).parameters)[:5] == \
+        ["x", "rois", "outh", "outw", "spatial_scale"]
+    assert list(inspect.signature(_roi_align_2d_yx).parameters)[:5] == \
+        ["x", "indices_and_rois", "outh", "outw", "spatial_scale"]
+    sig = inspect.signature(map_rois_to_fpn_levels)
+    assert list(sig.parameters) == ["rois", "k_min", "k_max"]
+    assert sig.parameters["k_min"].default == 0 and sig.parameters["k_max"].default == 4
+    for m in ("check_type_forward", "forward_cpu", "forward_gpu", "backward_cpu", "backward_gpu"):
+        assert callable(getattr(ROIAlign2D, m))
+    assert list(inspect.signature(pkg.FPNRoIPooling.__call__).parameters)[:5] == \
+        ["self", "x", "indices_and_rois", "levels", "spatial_scales"]
+    assert list(inspect.signature(pkg.FPNRoIPooling.predict_mask).parameters) == \
+        ["self", "levels", "indices_and_rois", "spatial_scales"]
+
+
+def test_pyramid_constants():
+    assert fpn.feat_strides == [4, 8, 16, 32, 64]          # feature_pyramid_network.py:9
+    assert fpn.spatial_scales == [1 / 4, 1 / 8, 1 / 16, 1 / 32, 1 / 64]
+    assert fpn.pyramid_shapes(2, 256, 800, 1333, 4) == \
+        [(2, 256, 200, 334), (2, 256, 100, 167), (2, 256, 50, 84), (2, 256, 25, 42)]
+
+
+def test_check_type_forward():
+    f = ROIAlign2D(7, 7, 0.25)
+    x = np.zeros((1, 4, 8, 8), np.float32)
+    r = np.zeros((3, 5), np.float32)
+    f.check_type_forward((x, r))
+    f.check_type_forward((torch.zeros(1, 4, 8, 8), torch.zeros(3, 5)))
+    for bad in [(x,), (x.astype(np.float64), r), (x[0], r), (x, r.astype(np.int32)),
+                (x, r[:, :4]), (x, r[0])]:
+        with pytest.raises(InvalidType):
+            f.check_type_forward(bad)
+
+
+def test_level_thresholds_are_cached_monotone_and_reference_exact():
+    t = _engine.level_thresholds()
+    assert t is _engine.level_thresholds()
+    assert list(np.array(t, np.float32).view(np.uint32)) == \
+        [0x4443ff31, 0x4543ff98, 0x4643ffc9, 0x4743ffe4]
+    assert all(b > a for a, b in zip(t, t[1:]))
+
+
+def test_out_size_normalisation():
+    assert _engine._norm_sizes([7]) == [(7, 7)]
+    assert _engine._norm_sizes([(5, 7), 14]) == [(5, 7), (14, 14)]
+    with pytest.raises(ValueError):
+        _engine._norm_sizes([7, 14, 28])
+
+
+def test_sharding_by_image():
+    rois = np.zeros((10, 5), np.float32)
+    rois[:, 0] = [0, 0, 1, 1, 2, 2, 3, 3, 4, 4]
+    rois[:, 1] = np.arange(10)
+    assert _sharding.images_of_rank(5, 2, 0) == [0, 2, 4]
+    assert _sharding.images_of_rank(5, 2, 1) == [1, 3]
+    seen = []
+    for rank in range(2):
+        local, rows = _sharding.shard_rois(rois, 5, 2, rank)
+        assert np.array_equal(local[:, 1], rois[rows, 1])
+        assert set(local[:, 0]) == set(range(len(_sharding.images_of_rank(5, 2, rank))))
+        seen += list(rows)
+    assert sorted(seen) == list(range(10))
+    assert _sharding.max_over_ranks(3.5) == 3.5
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from chainer_maskrcnn_b200 import _sharding
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rois = np.zeros((12, 5), np.float32); rois[:, 0] = np.repeat(np.arange(6), 2)
+local, rows = _sharding.shard_rois(rois, 6, world, rank)
+n = _sharding.sum_over_ranks(len(rows))
+t = _sharding.max_over_ranks(1.0 + rank)
+assert n == 12, n
+assert t == float(world), t
+assert sorted(set(local[:, 0])) == [0, 1, 2]
+dist.barrier()
+if rank == 0:
+    print("GLOO_OK", n, t)
+dist.destroy_process_group()
+"""
+
+
+def test_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+        capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "GLOO_OK 12.0 2.0" in out.stdout
