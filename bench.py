@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- FPN multi-level RoIAlign fwd+bwd throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one pass of the hot path over one synthetic batch: plan (level
+assignment + binning) + fused forward + backward (zero-fill + scatter).  The
+workload is BASELINE.json configs[1] (mask head 14x14, 2 images at 1333x800,
+2048 RoIs/image, P2-P5, 256 channels fp32) per GPU; with N > 1 every rank runs
+that workload on its own images (sharded by image, no data-path collective,
+weak scaling) and NCCL only reduces the timings.
+
+Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import synth  # noqa: E402
+
+METRIC = "roialign_fwd_bwd_throughput"
+UNIT = "RoIs/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=1, help="index into BASELINE.json configs (0..3)")
+    ap.add_argument("--sampling-ratio", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-rois", type=int, default=0, help="0 = sized automatically")
+    ap.add_argument("--tune", default="", help="comma list key=value for rpool_set_tuning")
+    return ap.parse_args()
+
+
+def workload(cfg_id, rank):
+    cfg = dict(synth.CONFIGS[cfg_id])
+    rng = np.random.RandomState(cfg_id + 1000 * rank)
+    L = cfg["n_levels"]
+    shapes = synth.pyramid_shapes(cfg["n_images"], cfg["channels"], cfg["height"], cfg["width"], L)
+    rois = synth.make_rois(rng, cfg["n_images"], cfg["rois_per_image"], cfg["height"], cfg["width"],
+                           aspect_range=cfg["aspect"])
+    scales = [1.0 / s for s in synth.STRIDES[:L]]
+    return cfg, rng, shapes, rois, scales
+
+
+def algorithmic_bytes(cfg, shapes, rois, levels, scales, S):
+    """fwd = O + U*C*4 + 20R; bwd = O + F + 20R."""
+    C = cfg["channels"]
+    R = rois.shape[0]
+    O = sum(R * C * P * P * 4 for P in cfg["out_sizes"])
+    F = sum(int(np.prod(s)) * 4 for s in shapes)
+    U = synth.window_cells_touched(rois, levels, shapes, scales, max(cfg["out_sizes"]) * max(S, 1))
+    return dict(O=O, F=F, U_bytes=U * C * 4, fwd=O + U * C * 4 + 20 * R, bwd=O + F + 20 * R)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:  # noqa: BLE001
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle port (and the reference's own C++ forward) on the host cores
+# ---------------------------------------------------------------------------
+_CPU_DATA = {}
+
+
+def cpu_arm(cfg_id, S, sample_rois, repeats=1):
+    """Times the CPU restatement of the reference path (oracle/, all host threads)
+    on a bounded sample of the same workload.  Returns (rois_per_s, info)."""
+    import oracle
+    if cfg_id not in _CPU_DATA:
+        cfg, rng, shapes, rois, scales = workload(cfg_id, 0)
+        feats = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+        _CPU_DATA[cfg_id] = (cfg, rng, shapes, rois, scales, feats)
+    cfg, rng, shapes, rois, scales, feats = _CPU_DATA[cfg_id]
+    threads = oracle.max_threads()
+    if sample_rois <= 0:
+        sample_rois = min(rois.shape[0], 4096)
+    sample_rois = min(sample_rois, rois.shape[0])
+    sel = np.sort(np.random.RandomState(99).choice(rois.shape[0], sample_rois, replace=False))
+    sub = rois[sel]
+    levels = oracle.levels_for_pyramid(sub[:, 1:], cfg["n_levels"])
+    mode = "chainer" if S == 1 else "caffe2"
+    gys = [synth.make_gy(np.random.RandomState(7), sub.shape[0], cfg["channels"], P)
+           for P in cfg["out_sizes"]]
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for P in cfg["out_sizes"]:
+            oracle.fpn_forward(feats, sub, levels, scales, P, mode, S, threads=threads)
+        t1 = time.perf_counter()
+        for g in gys:
+            oracle.fpn_backward(g, shapes, sub, levels, scales, mode, S, threads=threads)
+        t2 = time.perf_counter()
+        if best is None or (t2 - t0) < best[0]:
+            best = (t2 - t0, t1 - t0, t2 - t1)
+    info = {
+        "value": sub.shape[0] / best[0], "unit": UNIT, "cores": threads, "kind": "port",
+        "sample": "%d of %d RoIs of %s (drawn without replacement, seed 99); C port of the "
+                  "reference path (oracle/roialign_oracle.c, %s semantics, sampling_ratio %d), "
+                  "OpenMP over RoIs (fwd) / channels (bwd); fwd %.3f s + bwd %.3f s"
+                  % (sub.shape[0], rois.shape[0], cfg["name"], mode, S, best[1], best[2]),
+        "fwd_s": best[1], "bwd_s": best[2],
+    }
+    if oracle.have_ref() and len(cfg["out_sizes"]) == 1:
+        # the reference's own compiled C++ forward, single-threaded as shipped
+        n = min(sub.shape[0], 128)
+        rois_xy = oracle.roi_yx_to_xy(sub[:n])
+        t0 = time.perf_counter()
+        P = cfg["out_sizes"][0]
+        for l in range(cfg["n_levels"]):
+            m = np.nonzero(levels[:n] == l)[0]
+            if m.size:
+                oracle.ref_caffe2_forward(feats[l], rois_xy[m], P, P, scales[l], max(S, 1))
+        info["reference_cpp_forward_rois_per_s_1thread"] = n / (time.perf_counter() - t0)
+    return info["value"], info
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    sample = args.cpu_sample_rois if args.cpu_sample_rois > 0 else 1024
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_arm(args.config, args.sampling_ratio, min(sample, 64))
+    vals, info = [], None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, info = cpu_arm(args.config, args.sampling_ratio, sample)
+        vals.append(v)
+    dt = time.perf_counter() - t0
+    cfg = synth.CONFIGS[args.config]
+    value = float(np.mean(vals))
+    info["value"] = value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": cfg["name"], "sampling_ratio": args.sampling_ratio,
+                   "note": "CPU arm: bounded sample per step on the host cores"},
+        "cpu_baseline": info,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import chainer_maskrcnn_b200 as pkg
+    from chainer_maskrcnn_b200 import _engine, _lib, _sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        _lib.set_tuning(**{k: int(v)})
+
+    S = args.sampling_ratio
+    cfg, rng, shapes, rois_np, scales = workload(args.config, rank)
+    C, R = cfg["channels"], rois_np.shape[0]
+    sizes = cfg["out_sizes"]
+    # features live in HBM channels-last (the layout B200 convolutions produce)
+    feats = [torch.randn(s, device=device, dtype=torch.float32,
+                         generator=torch.Generator(device=device).manual_seed(17 + l + 100 * rank))
+             .contiguous(memory_format=torch.channels_last) for l, s in enumerate(shapes)]
+    rois = torch.from_numpy(rois_np).to(device)
+    gys = [(torch.rand((R, C, P, P), device=device, dtype=torch.float32) * 2 - 1)
+           .contiguous(memory_format=torch.channels_last) for P in sizes]
+    grads = [torch.empty(s, device=device, dtype=torch.float32,
+                         memory_format=torch.channels_last) for s in shapes]
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        outs, plan = _engine.forward(feats, rois, None, scales, sizes, sampling_ratio=S,
+                                     roi_format=_lib.ROI_YX)
+        if ev:
+            ev[1].record()
+        _engine.backward(plan, gys, out=grads)
+        if ev:
+            ev[2].record()
+        return outs
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    K = args.steps
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = _lib.launch_count()
+    e0.record()
+    for k in range(K):
+        step(evs[k])
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = _sharding.max_over_ranks(e0.elapsed_time(e1), device)
+    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    bwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    fwd_ms_max = _sharding.max_over_ranks(fwd_ms, device)
+    bwd_ms_max = _sharding.max_over_ranks(bwd_ms, device)
+    total_rois = _sharding.sum_over_ranks(R, device)
+    value = total_rois * K / (total_ms * 1e-3)
+
+    # ---- end to end through the public host-array API ---------------------
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda t: t.cpu().contiguous().pin_memory()
+        feats_h = [pin(f).numpy() for f in feats]           # NCHW host arrays, as the reference holds them
+        rois_h = pin(rois).numpy()
+        gys_h = [pin(g).numpy() for g in gys]
+        h2d = sum(a.nbytes for a in feats_h) + rois_h.nbytes + sum(a.nbytes for a in gys_h)
+        d2h = sum(a.nbytes for a in gys_h) + sum(a.nbytes for a in feats_h)
+        pkg.fpn_roi_align_host(feats_h, rois_h, None, scales, sizes, S, gys=gys_h)   # warm-up
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            pooled, g = pkg.fpn_roi_align_host(feats_h, rois_h, None, scales, sizes, S, gys=gys_h)
+        torch.cuda.synchronize()
+        dt = _sharding.max_over_ranks(time.perf_counter() - t0, device)
+        e2e = {"value": total_rois * args.e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": 1e3 * dt / args.e2e_steps,
+               "api": "chainer_maskrcnn_b200.fpn_roi_align_host (pinned NumPy in, NumPy out; "
+                      "NCHW->NHWC conversion on the device inside the timed region)"}
+        del feats_h, gys_h, pooled, g
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    levels_np = _engine.read_plan(_engine.make_plan(shapes, rois, None, scales, sizes, S))[0]
+    ab = algorithmic_bytes(cfg, shapes, rois_np, levels_np, scales, S)
+    peak, peak_src = measured_peak()
+    dom = "backward" if bwd_ms >= fwd_ms else "forward"
+    dom_ms = bwd_ms if dom == "backward" else fwd_ms
+    dom_bytes = ab["bwd"] if dom == "backward" else ab["fwd"]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None, "peak_source": peak_src,
+        "kernel": ("rpool_zero_kernel + rpool_backward_kernel" if dom == "backward"
+                   else "rpool_plan_kernel + rpool_forward_kernel"),
+        "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms,
+        "forward": {"ms": fwd_ms, "bytes": int(ab["fwd"]),
+                    "GBps": ab["fwd"] / (fwd_ms * 1e-3) / 1e9,
+                    "frac": ab["fwd"] / (fwd_ms * 1e-3) / 1e9 / peak},
+        "backward": {"ms": bwd_ms, "bytes": int(ab["bwd"]),
+                     "GBps": ab["bwd"] / (bwd_ms * 1e-3) / 1e9,
+                     "frac": ab["bwd"] / (bwd_ms * 1e-3) / 1e9 / peak},
+        "fwd_plus_bwd": {"bytes": int(ab["fwd"] + ab["bwd"]),
+                         "GBps": (ab["fwd"] + ab["bwd"]) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9,
+                         "frac": (ab["fwd"] + ab["bwd"]) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak},
+    }
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            import oracle
+            oracle.build()
+            _, cpu = cpu_arm(args.config, S, args.cpu_sample_rois, repeats=3)
+        except Exception as e:  # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": cfg["name"] + " per GPU", "baseline_config_index": args.config,
+            "rois_per_gpu": R, "channels": C, "out_sizes": sizes, "sampling_ratio": S,
+            "levels": "P2-P%d, assigned on device by the reference rule" % (cfg["n_levels"] + 1),
+            "layout": "channels-last features/pooled/gradients resident in HBM",
+            "step": "rpool_plan + rpool_forward + rpool_backward (zero-fill included)",
+            "l2": "no flush: one step touches %.0f MB >> 126 MB L2"
+                  % ((ab["O"] * 2 + ab["F"] * 2) / 1e6),
+            "sharding": "by image, one process per GPU, no data-path collective",
+            "tuning": {k: _lib.get_tuning(k) for k in ("smem_bytes", "threads", "order", "force_path")},
+        },
+        "fwd_ms": fwd_ms_max, "bwd_ms": bwd_ms_max,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

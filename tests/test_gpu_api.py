@@ -1,0 +1,156 @@
+"""GPU: the reference-shaped Python API (functions/, model/) on top of the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import synth
+import chainer_maskrcnn_b200 as pkg
+from chainer_maskrcnn_b200 import _lib
+from chainer_maskrcnn_b200.functions.roi_align.roi_align_2d import ROIAlign2D, roi_align_2d
+from chainer_maskrcnn_b200.functions.roi_align_2d_yx import _roi_align_2d_yx
+
+pytestmark = pytest.mark.gpu
+
+
+def _fixture(seed=0, N=3, C=32, H=12, W=8):
+    # the reference test's fixture (test_roi_align_2d.py:17-37) with a fixed seed
+    rng = np.random.RandomState(seed)
+    x = np.arange(N * C * H * W, dtype=np.float32).reshape(N, C, H, W)
+    rng.shuffle(x)
+    x = (2 * x / x.size - 1).astype(np.float32)
+    rois = np.tile(np.array([[0, 1, 1, 6, 6], [2, 6, 2, 7, 11], [1, 3, 1, 5, 10], [0, 3, 3, 3, 3]],
+                            np.float32), (15, 1))
+    gy = rng.uniform(-1, 1, (rois.shape[0], C, 5, 7)).astype(np.float32)
+    return x, rois, gy, 5, 7, 0.6
+
+
+def test_forward_shape_dtype_and_tuple_conventions():
+    x, rois, gy, outh, outw, scale = _fixture()
+    f = ROIAlign2D(outh, outw, scale)
+    out = f.forward_gpu((torch.from_numpy(x).cuda(), torch.from_numpy(rois).cuda()))
+    assert isinstance(out, tuple) and len(out) == 1                 # roi_align_2d.py:146
+    assert out[0].dtype == torch.float32 and tuple(out[0].shape) == gy.shape
+    assert f._bottom_data_shape == x.shape                           # roi_align_2d.py:94
+    back = f.backward_gpu((None, torch.from_numpy(rois).cuda()), (torch.from_numpy(gy).cuda(),))
+    assert isinstance(back, tuple) and len(back) == 2 and back[1] is None   # :281
+    assert tuple(back[0].shape) == x.shape
+    assert oracle.rel_err(out[0].cpu().numpy(), oracle.forward_chainer(x, rois, outh, outw, scale)) <= 1e-5
+    assert oracle.rel_err(back[0].cpu().numpy(),
+                          oracle.backward_chainer(gy, rois, x.shape, scale)) <= 1e-4
+
+
+def test_autograd_matches_oracle_and_numeric_gradient():
+    x, rois, gy, outh, outw, scale = _fixture(C=4)
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    y = roi_align_2d(xt, torch.from_numpy(rois).cuda(), outh, outw, scale)
+    y.backward(torch.from_numpy(gy).cuda())
+    g = xt.grad.cpu().numpy()
+    assert oracle.rel_err(g, oracle.backward_chainer(gy, rois, x.shape, scale)) <= 1e-4
+    # numeric gradient on the device op at the reference's tolerances (:37)
+    rng = np.random.RandomState(1)
+    eps = 1e-2
+    r = torch.from_numpy(rois).cuda()
+    gyt = torch.from_numpy(gy).cuda()
+    for _ in range(10):
+        idx = tuple(rng.randint(s) for s in x.shape)
+        xp, xm = x.copy(), x.copy()
+        xp[idx] += eps
+        xm[idx] -= eps
+        fp = roi_align_2d(torch.from_numpy(xp).cuda(), r, outh, outw, scale).double()
+        fm = roi_align_2d(torch.from_numpy(xm).cuda(), r, outh, outw, scale).double()
+        num = float(((fp - fm) * gyt).sum() / (2 * eps))
+        assert abs(num - g[idx]) <= 1e-3 + 1e-2 * abs(num)
+
+
+def test_host_arrays_roundtrip_through_gpu():
+    x, rois, gy, outh, outw, scale = _fixture()
+    f = ROIAlign2D(outh, outw, scale)
+    (y,) = f.forward_cpu((x, rois))
+    assert isinstance(y, np.ndarray) and y.dtype == np.float32 and y.shape == gy.shape
+    assert oracle.rel_err(y, oracle.forward_chainer(x, rois, outh, outw, scale)) <= 1e-5
+    gx, none = f.backward_cpu((x, rois), (gy,))
+    assert none is None and isinstance(gx, np.ndarray) and gx.shape == x.shape
+    assert oracle.rel_err(gx, oracle.backward_chainer(gy, rois, x.shape, scale)) <= 1e-4
+    y2 = roi_align_2d(x, rois, outh, outw, scale)
+    assert np.array_equal(np.asarray(y2), np.asarray(y))
+    (y3,) = f.forward((x, rois))
+    assert np.array_equal(np.asarray(y3), np.asarray(y))
+
+
+def test_yx_wrapper_equals_permuted_call():
+    x, rois, gy, outh, outw, scale = _fixture()
+    yx = rois[:, [0, 2, 1, 4, 3]].copy()
+    a = _roi_align_2d_yx(torch.from_numpy(x).cuda(), torch.from_numpy(yx).cuda(), outh, outw, scale)
+    b = roi_align_2d(torch.from_numpy(x).cuda(), torch.from_numpy(rois).cuda(), outh, outw, scale)
+    assert torch.equal(a, b)
+    # the SURVEY 8(c) known answer for the wrapper
+    field = (10 * np.arange(6)[:, None] + np.arange(6)[None, :]).astype(np.float32)[None, None]
+    out = _roi_align_2d_yx(torch.from_numpy(field).cuda(),
+                           torch.tensor([[0, 4, 8, 20, 24]], dtype=torch.float32).cuda(), 2, 2, 0.25)
+    assert out.flatten().tolist() == [23.0, 25.0, 43.0, 45.0]
+
+
+def test_fused_head_call_replaces_the_per_roi_loop():
+    rng = np.random.RandomState(3)
+    n_img, C, H, W, L = 2, 32, 160, 224, 5                 # five levels: p2..p6
+    feats = synth.make_pyramid(rng, n_img, C, H, W, L)
+    rois = synth.make_rois(rng, n_img, 50, H, W, size_range=(8.0, 300.0))
+    from chainer_maskrcnn_b200.model.extractor.feature_pyramid_network import spatial_scales as scales
+    ft = [torch.from_numpy(f).cuda().requires_grad_(True) for f in feats]
+    rt = torch.from_numpy(rois).cuda()
+    levels_f = pkg.map_rois_to_fpn_levels(rt[:, 1:])        # float32, like the reference
+    assert levels_f.dtype == torch.float32
+    want_lv = oracle.map_rois_to_fpn_levels(rois[:, 1:])
+    assert np.array_equal(levels_f.cpu().numpy(), want_lv)
+    pooler = pkg.FPNRoIPooling(7, 14)
+    box, mask = pooler(ft, rt, levels_f, scales, train=True)
+    lv = np.clip(want_lv, 0, L - 1).astype(np.int32)
+    assert oracle.rel_err(box.detach().cpu().numpy(), oracle.fpn_forward(feats, rois, lv, scales, 7)) <= 1e-5
+    assert oracle.rel_err(mask.detach().cpu().numpy(), oracle.fpn_forward(feats, rois, lv, scales, 14)) <= 1e-5
+    gb = synth.make_gy(rng, rois.shape[0], C, 7)
+    gm = synth.make_gy(rng, rois.shape[0], C, 14)
+    (box * torch.from_numpy(gb).cuda()).sum().backward(retain_graph=True)
+    (mask * torch.from_numpy(gm).cuda()).sum().backward()
+    shapes = [f.shape for f in feats]
+    w7 = oracle.fpn_backward(gb, shapes, rois, lv, scales)
+    w14 = oracle.fpn_backward(gm, shapes, rois, lv, scales)
+    for l in range(L):
+        assert oracle.rel_err(ft[l].grad.cpu().numpy(), w7[l] + w14[l]) <= 1e-4
+    # test mode: box only, features cached for predict_mask (fpn_roi_mask_head.py:85-95)
+    box2 = pooler(ft, rt, levels_f, scales, train=False)
+    assert torch.equal(box2, box)
+    mask2 = pooler.predict_mask(levels_f, rt, scales)
+    assert torch.equal(mask2, mask)
+    # levels=None: assigned on the device, same result
+    box3 = pkg.fpn_roi_align(ft, rt, None, scales, 7)
+    assert torch.equal(box3, box)
+
+
+def test_host_fused_call_and_launch_counter():
+    rng = np.random.RandomState(4)
+    feats = synth.make_pyramid(rng, 1, 16, 128, 128, 4)
+    rois = synth.make_rois(rng, 1, 40, 128, 128, size_range=(8.0, 120.0))
+    scales = [1.0 / s for s in synth.STRIDES[:4]]
+    gys = [synth.make_gy(rng, 40, 16, 7)]
+    n0 = _lib.launch_count()
+    pooled, grads = pkg.fpn_roi_align_host(feats, rois, None, scales, [7], 2, gys=gys)
+    assert _lib.launch_count() - n0 >= 4 + 3          # 4 layout conversions + plan + fwd + zero + bwd
+    lv = oracle.levels_for_pyramid(rois[:, 1:], 4)
+    assert oracle.rel_err(pooled[0], oracle.fpn_forward(feats, rois, lv, scales, 7, "caffe2", 2)) <= 1e-5
+    want = oracle.fpn_backward(gys[0], [f.shape for f in feats], rois, lv, scales, "caffe2", 2)
+    for g, w in zip(grads, want):
+        assert g.shape == w.shape and oracle.rel_err(g, w) <= 1e-4
+
+
+def test_errors_are_loud():
+    x = torch.zeros(1, 4, 8, 8).cuda()
+    r = torch.zeros(2, 5).cuda()
+    with pytest.raises(_lib.RpoolError):
+        ROIAlign2D(2, 2, 1.0, sampling_ratio=100).forward_gpu((x, r))
+    with pytest.raises(TypeError):
+        roi_align_2d(x.double(), r, 2, 2, 1.0)
+    with pytest.raises(TypeError):
+        roi_align_2d(x, r[:, :4], 2, 2, 1.0)
+    with pytest.raises(TypeError):
+        roi_align_2d(x.cpu(), r, 2, 2, 1.0)

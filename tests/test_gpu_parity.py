@@ -1,0 +1,376 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on
+the same seeded inputs, against the committed golden fixtures, and at
+BASELINE.json's full sizes.
+
+Tolerances (BASELINE.json north_star), metric max|a-b| / max|b|:
+    forward  <= 1e-5      backward <= 1e-4 (atomic reordering)
+    level assignment and output<->RoI order: bit-exact
+The generic kernel path replays the reference's operation order and is
+checked bit-for-bit in the forward direction.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import synth
+from chainer_maskrcnn_b200 import _engine, _lib
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 1e-5
+BWD_TOL = 1e-4
+PATHS = {"auto": _lib.PATH_AUTO, "generic": _lib.PATH_GENERIC, "direct": _lib.PATH_DIRECT,
+         "staged": _lib.PATH_STAGED}
+
+
+@pytest.fixture(autouse=True)
+def _reset_tuning():
+    defaults = {k: _lib.get_tuning(k) for k in ("smem_bytes", "threads", "order", "force_path")}
+    yield
+    _lib.set_tuning(**defaults)
+
+
+def dev(a, channels_last=False):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    if channels_last and t.dim() == 4:
+        t = t.contiguous(memory_format=torch.channels_last)
+    return t
+
+
+def host(t):
+    return np.ascontiguousarray(t.detach().cpu().numpy())
+
+
+def run_fused(feats, rois_yx, levels, scales, out_sizes, S=1, mode=None, channels_last=True,
+              gys=None, levels_dtype=np.int32):
+    f = [dev(x, channels_last) for x in feats]
+    lv = None if levels is None else dev(np.asarray(levels).astype(levels_dtype))
+    outs, plan = _engine.forward(f, dev(rois_yx), lv, scales, out_sizes, sampling_ratio=S,
+                                 coord_mode=mode, roi_format=_lib.ROI_YX)
+    for o in outs:
+        assert o.is_contiguous(memory_format=torch.channels_last) or o.numel() == 0 or o.shape[1] == 1
+    grads = None
+    if gys is not None:
+        grads = [host(g) for g in _engine.backward(plan, [dev(g) for g in gys])]
+    torch.cuda.synchronize()
+    return [host(o) for o in outs], grads, plan
+
+
+def oracle_fused(feats, rois_yx, levels, scales, out_sizes, S, mode_name, gys=None):
+    outs = [oracle.fpn_forward(feats, rois_yx, levels, scales, P, mode_name, S, threads=8)
+            for P in out_sizes]
+    grads = None
+    if gys is not None:
+        grads = [np.zeros_like(f) for f in feats]
+        for g in gys:
+            part = oracle.fpn_backward(g, [f.shape for f in feats], rois_yx, levels, scales,
+                                       mode_name, S, threads=8)
+            for l in range(len(feats)):
+                grads[l] += part[l]
+    return outs, grads
+
+
+def make_case(seed, n_img=2, C=64, Himg=256, Wimg=320, L=4, per_img=150, size=(8.0, 300.0),
+              aspect=(0.5, 2.0)):
+    rng = np.random.RandomState(seed)
+    feats = synth.make_pyramid(rng, n_img, C, Himg, Wimg, L)
+    rois = synth.make_rois(rng, n_img, per_img, Himg, Wimg, size_range=size, aspect_range=aspect)
+    rng.shuffle(rois)  # interleave images: the schedule must not depend on input order
+    levels = oracle.levels_for_pyramid(rois[:, 1:], L)
+    scales = [1.0 / s for s in synth.STRIDES[:L]]
+    return rng, feats, rois, levels, scales
+
+
+# ---------------------------------------------------------------------------
+# golden fixtures generated from the unmodified reference
+# ---------------------------------------------------------------------------
+def test_golden_reference_fixture_single_level_op(golden_dir):
+    from chainer_maskrcnn_b200 import ROIAlign2D
+    d = np.load(os.path.join(golden_dir, "reference_fixture.npz"))
+    outh, outw, scale = int(d["outh"]), int(d["outw"]), float(d["scale"])
+    x, rois, gy = dev(d["x"]), dev(d["rois"]), dev(d["gy"])
+    for path in ("auto", "generic", "direct"):
+        _lib.set_tuning(force_path=PATHS[path])
+        f = ROIAlign2D(outh, outw, scale)
+        (y,) = f.forward_gpu((x, rois))
+        assert y.dtype == torch.float32 and tuple(y.shape) == tuple(d["gy"].shape)
+        assert oracle.rel_err(host(y), d["y"]) <= FWD_TOL, path
+        if path == "generic":
+            # C = 16 is a multiple of 4 but the generic path was forced: reference op order
+            assert np.array_equal(host(y), d["y"])
+        gx, none = f.backward_gpu((None, rois), (gy,))
+        assert none is None
+        assert oracle.rel_err(host(gx), d["gx"]) <= BWD_TOL, path
+        for S in (1, 2, 3):
+            (y2,), _ = _engine.forward([x], rois, None, [scale], [(outh, outw)], S,
+                                       _lib.COORD_CAFFE2, _lib.ROI_XY)
+            assert oracle.rel_err(host(y2), d["y_caffe2_s%d" % S]) <= FWD_TOL, (path, S)
+            if path == "generic":
+                assert np.array_equal(host(y2), d["y_caffe2_s%d" % S])
+
+
+def test_golden_fpn_small_fused_two_heads(golden_dir):
+    d = np.load(os.path.join(golden_dir, "fpn_small.npz"))
+    feats = [d["feat%d" % l] for l in range(4)]
+    scales = [float(s) for s in d["scales"]]
+    for levels in (None, d["levels"], d["levels_f32"]):
+        ldt = np.float32 if levels is not None and levels.dtype == np.float32 else np.int32
+        for cl in (True, False):
+            outs, grads, plan = run_fused(feats, d["rois"], levels, scales, [7, 14], 1, None, cl,
+                                          gys=[d["gy7"], d["gy14"]], levels_dtype=ldt)
+            lv, order = _engine.read_plan(plan)
+            assert np.array_equal(lv, d["levels"])             # bit-exact level assignment
+            assert oracle.rel_err(outs[0], d["y7"]) <= FWD_TOL
+            assert oracle.rel_err(outs[1], d["y14"]) <= FWD_TOL
+            for l in range(4):
+                want = d["gx7_l%d" % l] + d["gx14_l%d" % l]
+                assert oracle.rel_err(grads[l], want) <= BWD_TOL, l
+    outs, _, _ = run_fused(feats, d["rois"], d["levels"], scales, [7, 14], 2)
+    assert oracle.rel_err(outs[0], d["y7_caffe2_s2"]) <= FWD_TOL
+    assert oracle.rel_err(outs[1], d["y14_caffe2_s2"]) <= FWD_TOL
+
+
+def test_golden_levels_bit_exact(golden_dir):
+    d = np.load(os.path.join(golden_dir, "levels.npz"))
+    got = host(_engine.assign_levels(dev(d["boxes"])))
+    assert got.dtype == np.float32 and np.array_equal(got, d["levels"])
+    got3 = host(_engine.assign_levels(dev(d["boxes"]), k_max=3))
+    assert np.array_equal(got3, d["levels_kmax3"])
+    from chainer_maskrcnn_b200 import map_rois_to_fpn_levels
+    assert np.array_equal(host(map_rois_to_fpn_levels(dev(d["boxes"]))), d["levels"])
+    assert np.array_equal(map_rois_to_fpn_levels(d["boxes"]), d["levels"])   # host arrays in/out
+
+
+def test_levels_random_million_bit_exact():
+    rng = np.random.RandomState(11)
+    n = 1_000_000
+    b = np.zeros((n, 4), np.float32)
+    b[:, :2] = rng.uniform(0, 1400, (n, 2))
+    b[:, 2:] = b[:, :2] + np.exp(rng.uniform(np.log(0.5), np.log(1400), (n, 2))).astype(np.float32)
+    want = oracle.map_rois_to_fpn_levels(b)
+    got = host(_engine.assign_levels(dev(b)))
+    assert np.array_equal(got, want)
+    gi = host(_engine.assign_levels(dev(b), k_cap=3, as_int=True))
+    assert gi.dtype == np.int32 and np.array_equal(gi, np.clip(want, 0, 3).astype(np.int32))
+
+
+# ---------------------------------------------------------------------------
+# seeded random cases against the oracle, every kernel path
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("path,smem_kb", [("auto", 74), ("generic", 74), ("direct", 74),
+                                          ("staged", 74), ("staged", 24), ("auto", 12)])
+@pytest.mark.parametrize("mode_name,S", [("chainer", 1), ("caffe2", 1), ("caffe2", 2), ("caffe2", 3)])
+def test_fused_vs_oracle(path, smem_kb, mode_name, S):
+    rng, feats, rois, levels, scales = make_case(seed=S * 7 + len(path))
+    _lib.set_tuning(force_path=PATHS[path], smem_bytes=smem_kb * 1024)
+    mode = _lib.COORD_CHAINER if mode_name == "chainer" else _lib.COORD_CAFFE2
+    sizes = [7, 14]
+    gys = [synth.make_gy(rng, rois.shape[0], feats[0].shape[1], P) for P in sizes]
+    outs, grads, plan = run_fused(feats, rois, levels, scales, sizes, S, mode, gys=gys)
+    want, wgrads = oracle_fused(feats, rois, levels, scales, sizes, S, mode_name, gys)
+    for o, w in zip(outs, want):
+        assert oracle.rel_err(o, w) <= FWD_TOL
+        if path == "generic":
+            assert np.array_equal(o, w)          # reference operation order
+    for g, w in zip(grads, wgrads):
+        assert oracle.rel_err(g, w) <= BWD_TOL
+
+
+@pytest.mark.parametrize("threads", [64, 128, 224, 512])
+def test_block_sizes(threads):
+    rng, feats, rois, levels, scales = make_case(seed=3, C=128, per_img=60)
+    _lib.set_tuning(threads=threads)
+    gys = [synth.make_gy(rng, rois.shape[0], 128, 14)]
+    outs, grads, _ = run_fused(feats, rois, levels, scales, [14], 2, gys=gys)
+    want, wgrads = oracle_fused(feats, rois, levels, scales, [14], 2, "caffe2", gys)
+    assert oracle.rel_err(outs[0], want[0]) <= FWD_TOL
+    for g, w in zip(grads, wgrads):
+        assert oracle.rel_err(g, w) <= BWD_TOL
+
+
+def test_rectangular_output_and_odd_channels():
+    # C = 6 is not a multiple of 4 -> generic path; (5,7) output as in the reference test
+    rng, feats, rois, levels, scales = make_case(seed=5, C=6, per_img=40)
+    gys = [rng.uniform(-1, 1, (rois.shape[0], 6, 5, 7)).astype(np.float32)]
+    f = [dev(x) for x in feats]
+    outs, plan = _engine.forward(f, dev(rois), dev(levels), scales, [(5, 7)])
+    grads = _engine.backward(plan, [dev(gys[0])])
+    rois_xy = oracle.roi_yx_to_xy(rois)
+    want = np.zeros((rois.shape[0], 6, 5, 7), np.float32)
+    for l in range(4):
+        sel = np.nonzero(levels == l)[0]
+        want[sel] = oracle.forward_chainer(feats[l], rois_xy[sel], 5, 7, scales[l])
+        wg = oracle.backward_chainer(gys[0][sel], rois_xy[sel], feats[l].shape, scales[l])
+        assert oracle.rel_err(host(grads[l]), wg) <= BWD_TOL
+    assert np.array_equal(host(outs[0]), want)
+    # same with C = 8 (fast path), rectangular
+    rng, feats, rois, levels, scales = make_case(seed=6, C=8, per_img=40)
+    outs, plan = _engine.forward([dev(x) for x in feats], dev(rois), dev(levels), scales, [(5, 7)])
+    rois_xy = oracle.roi_yx_to_xy(rois)
+    for l in range(4):
+        sel = np.nonzero(levels == l)[0]
+        w = oracle.forward_chainer(feats[l], rois_xy[sel], 5, 7, scales[l])
+        assert oracle.rel_err(host(outs[0])[sel], w) <= FWD_TOL
+
+
+def test_large_pooled_size_and_adaptive_sampling():
+    rng, feats, rois, levels, scales = make_case(seed=8, C=8, per_img=30)
+    # P = 40 > fast-path table size -> generic; S = 0 -> caffe2 adaptive grid -> generic
+    for P, S in ((40, 2), (7, 0), (3, 0)):
+        outs, _, _ = run_fused(feats, rois, levels, scales, [P], S, _lib.COORD_CAFFE2)
+        want, _ = oracle_fused(feats, rois, levels, scales, [P], S, "caffe2")
+        assert np.array_equal(outs[0], want[0]), (P, S)
+    gy = synth.make_gy(rng, rois.shape[0], 8, 7)
+    _, grads, _ = run_fused(feats, rois, levels, scales, [7], 0, _lib.COORD_CAFFE2, gys=[gy])
+    _, wg = oracle_fused(feats, rois, levels, scales, [7], 0, "caffe2", [gy])
+    for g, w in zip(grads, wg):
+        assert oracle.rel_err(g, w) <= BWD_TOL
+
+
+def test_wide_bins_single_level():
+    """The reference micro-benchmark shape (test_performance.py:19-25): 200 px RoIs
+    on a stride-1 map, 14x14 -> bins 14 cells wide (sliding window must jump)."""
+    rng = np.random.RandomState(9)
+    x = rng.standard_normal((1, 16, 224, 224)).astype(np.float32)
+    rois = np.array([[0, 0, 0, 200, 200], [0, 10.5, 3.25, 190, 222], [0, 100, 100, 101, 180]], np.float32)
+    from chainer_maskrcnn_b200 import roi_align_2d
+    for S in (1, 2):
+        y = roi_align_2d(dev(x), dev(rois), 14, 14, 1.0, sampling_ratio=S)
+        w = oracle.forward_chainer(x, rois, 14, 14, 1.0) if S == 1 else \
+            oracle.forward_caffe2(x, rois, 14, 14, 1.0, S)
+        assert oracle.rel_err(host(y), w) <= FWD_TOL
+
+
+def test_edge_cases_caffe2_borders_and_degenerate():
+    rng = np.random.RandomState(10)
+    x = rng.standard_normal((2, 8, 20, 27)).astype(np.float32)
+    rois = np.array([[0, -8, -8, 10, 10], [1, 40, 30, 70, 50], [0, -30, 5, -20, 9],
+                     [1, 10, 10, 10, 10], [0, 0, 0, 54, 40], [1, 53.9, 39.9, 54, 40],
+                     [0, 25, 18, 80, 70]], np.float32)       # xy format
+    gy = rng.uniform(-1, 1, (rois.shape[0], 8, 7, 7)).astype(np.float32)
+    for path in ("auto", "generic", "direct", "staged"):
+        _lib.set_tuning(force_path=PATHS[path])
+        for S in (1, 2):
+            outs, plan = _engine.forward([dev(x)], dev(rois), None, [0.5], [7], S,
+                                         _lib.COORD_CAFFE2, _lib.ROI_XY)
+            w = oracle.forward_caffe2(x, rois, 7, 7, 0.5, S)
+            assert oracle.rel_err(host(outs[0]), w) <= FWD_TOL, (path, S)
+            g = _engine.backward(plan, [dev(gy)])
+            wg = oracle.backward_caffe2(gy, rois, x.shape, 0.5, S)
+            assert oracle.rel_err(host(g[0]), wg) <= BWD_TOL, (path, S)
+    # chainer mode: degenerate boxes (double-precision stride branch) and negative origins
+    rois_c = np.array([[0, 3, 3, 3, 3], [1, 2.5, 4, 2.6, 9], [0, 1, 1, 1.2, 30], [1, -1.5, -0.75, 20, 12]],
+                      np.float32)
+    gyc = rng.uniform(-1, 1, (rois_c.shape[0], 8, 5, 7)).astype(np.float32)
+    for path in ("auto", "generic"):
+        _lib.set_tuning(force_path=PATHS[path])
+        outs, plan = _engine.forward([dev(x)], dev(rois_c), None, [0.5], [(5, 7)], 1,
+                                     _lib.COORD_CHAINER, _lib.ROI_XY)
+        w = oracle.forward_chainer(x, rois_c, 5, 7, 0.5)
+        assert oracle.rel_err(host(outs[0]), w) <= FWD_TOL
+        if path == "generic":
+            assert np.array_equal(host(outs[0]), w)
+        g = _engine.backward(plan, [dev(gyc)])
+        assert oracle.rel_err(host(g[0]), oracle.backward_chainer(gyc, rois_c, x.shape, 0.5)) <= BWD_TOL
+
+
+def test_empty_invalid_batch_and_level_clipping():
+    rng, feats, rois, levels, scales = make_case(seed=12, C=8, per_img=10)
+    f = [dev(x) for x in feats]
+    outs, plan = _engine.forward(f, dev(rois[:0]), dev(levels[:0]), scales, [7, 14])
+    assert tuple(outs[0].shape) == (0, 8, 7, 7) and tuple(outs[1].shape) == (0, 8, 14, 14)
+    grads = _engine.backward(plan, [dev(np.zeros((0, 8, 7, 7), np.float32)),
+                                    dev(np.zeros((0, 8, 14, 14), np.float32))])
+    assert all(float(g.abs().max()) == 0.0 for g in grads)      # zero-filled dense gradients
+    # out-of-range levels are clipped to the pyramid (maskrcnn.py:141); a batch index
+    # outside the tensor yields zeros and no gradient
+    lv = levels.copy()
+    lv[0], lv[1] = 9, -3
+    r2 = rois.copy()
+    r2[2, 0] = 7
+    outs, plan = _engine.forward(f, dev(r2), dev(lv), scales, [7])
+    want = oracle.fpn_forward(feats, np.delete(r2, 2, 0), np.clip(np.delete(lv, 2), 0, 3), scales, 7)
+    got = host(outs[0])
+    assert np.all(got[2] == 0)
+    assert oracle.rel_err(np.delete(got, 2, 0), want) <= FWD_TOL
+
+
+def test_schedule_is_stable_binning_and_rows_keep_input_order():
+    rng, feats, rois, levels, scales = make_case(seed=13, C=8, per_img=500)
+    for order_mode in (0, 1, 2):
+        _lib.set_tuning(order=order_mode)
+        outs, _, plan = run_fused(feats, rois, None, scales, [7])
+        lv, order = _engine.read_plan(plan)
+        assert np.array_equal(lv, levels)
+        img = rois[:, 0].astype(np.int64)
+        if order_mode == 0:
+            want = np.arange(len(lv))
+        elif order_mode == 1:
+            want = np.argsort(img * 4 + lv, kind="stable")
+        else:
+            want = np.argsort(img * 4 + (3 - lv), kind="stable")
+        assert np.array_equal(order, want.astype(np.int32))
+        # row r of the output is RoI r whatever the schedule (fpn_roi_mask_head.py:59-63)
+        ref_out = oracle.fpn_forward(feats, rois, levels, scales, 7)
+        assert oracle.rel_err(outs[0], ref_out) <= FWD_TOL
+        perm = rng.permutation(len(lv))
+        outs_p, _, _ = run_fused(feats, rois[perm], None, scales, [7])
+        assert np.array_equal(outs_p[0], outs[0][perm])
+
+
+def test_forward_is_run_to_run_identical_and_backward_within_tolerance():
+    rng, feats, rois, levels, scales = make_case(seed=14, per_img=200)
+    gy = synth.make_gy(rng, rois.shape[0], 64, 14)
+    a, ga, _ = run_fused(feats, rois, levels, scales, [14], 2, gys=[gy])
+    b, gb, _ = run_fused(feats, rois, levels, scales, [14], 2, gys=[gy])
+    assert np.array_equal(a[0], b[0])
+    for x, y in zip(ga, gb):
+        assert oracle.rel_err(x, y) <= BWD_TOL
+
+
+def test_layout_conversion_kernels():
+    rng = np.random.RandomState(15)
+    x = rng.standard_normal((3, 37, 19, 45)).astype(np.float32)
+    t = dev(x)
+    cl = _engine.to_channels_last(t)
+    assert cl.is_contiguous(memory_format=torch.channels_last)
+    assert np.array_equal(host(cl), x)
+    assert np.array_equal(host(cl.permute(0, 2, 3, 1).contiguous()), x.transpose(0, 2, 3, 1))
+    back = _engine.to_nchw_contiguous(cl)
+    assert back.is_contiguous() and np.array_equal(host(back), x)
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json sizes
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg_id,mode_name,S", [(0, "chainer", 1), (0, "caffe2", 2),
+                                                (1, "chainer", 1), (1, "caffe2", 2)])
+def test_full_size_configs(cfg_id, mode_name, S):
+    cfg = synth.CONFIGS[cfg_id]
+    rng = np.random.RandomState(cfg_id)
+    feats = synth.make_pyramid(rng, cfg["n_images"], cfg["channels"], cfg["height"], cfg["width"],
+                               cfg["n_levels"])
+    rois = synth.make_rois(rng, cfg["n_images"], cfg["rois_per_image"], cfg["height"], cfg["width"],
+                           aspect_range=cfg["aspect"])
+    L = cfg["n_levels"]
+    levels = oracle.levels_for_pyramid(rois[:, 1:], L)
+    scales = [1.0 / s for s in synth.STRIDES[:L]]
+    sizes = cfg["out_sizes"]
+    gys = [synth.make_gy(rng, rois.shape[0], cfg["channels"], P) for P in sizes]
+    mode = _lib.COORD_CHAINER if mode_name == "chainer" else _lib.COORD_CAFFE2
+    outs, grads, plan = run_fused(feats, rois, None, scales, sizes, S, mode, gys=gys)
+    lv, _ = _engine.read_plan(plan)
+    assert np.array_equal(lv, levels)
+    want, wgrads = oracle_fused(feats, rois, levels, scales, sizes, S, mode_name, gys)
+    for o, w in zip(outs, want):
+        assert oracle.rel_err(o, w) <= FWD_TOL
+    for g, w in zip(grads, wgrads):
+        assert oracle.rel_err(g, w) <= BWD_TOL
+    # adjoint identity <y, gy> == <x, gx> at full size (size-independent property)
+    lhs = sum(float((o.astype(np.float64) * g).sum()) for o, g in zip(outs, gys))
+    rhs = sum(float((f.astype(np.float64) * g).sum()) for f, g in zip(feats, grads))
+    scale = sum(float(np.abs(o.astype(np.float64) * g).sum()) for o, g in zip(outs, gys))
+    assert abs(lhs - rhs) <= 2e-7 * scale
