@@ -218,11 +218,21 @@ def test_rectangular_output_and_odd_channels():
 
 def test_large_pooled_size_and_adaptive_sampling():
     rng, feats, rois, levels, scales = make_case(seed=8, C=8, per_img=30)
-    # P = 40 > fast-path table size -> generic; S = 0 -> caffe2 adaptive grid -> generic
+    # P = 40 > fast-path table size -> generic path, which keeps the reference's
+    # operation order and is therefore bit-equal.  S = 0 (caffe2 adaptive grid,
+    # ceil(bin size) samples per side) takes the table path whenever a bin's
+    # footprint fits it: within tolerance there, bit-equal when forced generic.
     for P, S in ((40, 2), (7, 0), (3, 0)):
-        outs, _, _ = run_fused(feats, rois, levels, scales, [P], S, _lib.COORD_CAFFE2)
         want, _ = oracle_fused(feats, rois, levels, scales, [P], S, "caffe2")
-        assert np.array_equal(outs[0], want[0]), (P, S)
+        outs, _, _ = run_fused(feats, rois, levels, scales, [P], S, _lib.COORD_CAFFE2)
+        if P > 32:
+            assert np.array_equal(outs[0], want[0]), (P, S)
+        else:
+            assert oracle.rel_err(outs[0], want[0]) <= FWD_TOL, (P, S)
+        _lib.set_tuning(force_path=_lib.PATH_GENERIC)
+        outs, _, _ = run_fused(feats, rois, levels, scales, [P], S, _lib.COORD_CAFFE2)
+        _lib.set_tuning(force_path=_lib.PATH_AUTO)
+        assert np.array_equal(outs[0], want[0]), (P, S, "generic")
     gy = synth.make_gy(rng, rois.shape[0], 8, 7)
     _, grads, _ = run_fused(feats, rois, levels, scales, [7], 0, _lib.COORD_CAFFE2, gys=[gy])
     _, wg = oracle_fused(feats, rois, levels, scales, [7], 0, "caffe2", [gy])
