@@ -67,6 +67,8 @@ def to_channels_last(t):
     Zero-copy when it already is; otherwise one pass of rpool_nchw_to_nhwc."""
     if t.is_contiguous(memory_format=torch.channels_last):
         return t
+    if t.numel() == 0:
+        return t.contiguous(memory_format=torch.channels_last)
     src = t.contiguous()
     n, c, h, w = src.shape
     dst = torch.empty_like(src, memory_format=torch.channels_last)
@@ -76,8 +78,8 @@ def to_channels_last(t):
 
 def to_nchw_contiguous(t):
     """Logical (N,C,H,W) tensor in channels-last memory -> NCHW-contiguous copy."""
-    if t.is_contiguous():
-        return t
+    if t.is_contiguous() or t.numel() == 0:
+        return t.contiguous()
     if not t.is_contiguous(memory_format=torch.channels_last):
         t = to_channels_last(t)
     n, c, h, w = t.shape

@@ -15,7 +15,7 @@ MAX_HEADS = 2
 NHWC, NCHW = 0, 1
 ROI_XY, ROI_YX = 0, 1
 COORD_CHAINER, COORD_CAFFE2 = 0, 1
-PATH_AUTO, PATH_GENERIC, PATH_DIRECT, PATH_STAGED = 0, 1, 2, 3
+PATH_AUTO, PATH_GENERIC, PATH_TABLE = 0, 1, 2
 
 _STATUS = {1: "invalid argument", 2: "unsupported", 3: "workspace", 4: "CUDA error"}
 

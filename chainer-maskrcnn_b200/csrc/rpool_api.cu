@@ -18,7 +18,7 @@ thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 
 // tuning knobs (process-wide; experiments only)
-std::atomic<int> g_smem_bytes{74 * 1024};
+std::atomic<int> g_strip_cols{12};
 std::atomic<int> g_threads{256};
 std::atomic<int> g_order{1};
 std::atomic<int> g_force_path{kPathAuto};
@@ -115,7 +115,11 @@ int validate(const rpool_problem *p, void *ws, size_t ws_size, bool need_pooled)
     return RPOOL_OK;
 }
 
-int fill_params(const rpool_problem *p, const Workspace &w, KParams &k)
+constexpr int kMaxSmem = 227 * 1024;
+
+// Fills the kernel parameter block; returns the dynamic shared memory the
+// launch needs (control block + per-warp strips [+ transposed tables]).
+int fill_params(const rpool_problem *p, const Workspace &w, bool bwd, int threads, KParams &k)
 {
     memset(&k, 0, sizeof(k));
     for (int l = 0; l < p->n_levels; ++l) {
@@ -135,19 +139,25 @@ int fill_params(const rpool_problem *p, const Workspace &w, KParams &k)
     k.roi_level = w.levels;
     k.order = w.order;
     k.n_heads = p->n_heads;
+    int sum_pw = 0;
     for (int h = 0; h < p->n_heads; ++h) {
         k.PH[h] = p->out_h[h];
         k.PW[h] = p->out_w[h];
         k.pooled[h] = static_cast<float *>(p->pooled[h]);
+        sum_pw += p->out_w[h] <= kPBwd ? p->out_w[h] : 0;
     }
     k.S = p->sampling_ratio;
     k.mode = p->coord_mode;
     k.force_path = g_force_path.load();
     const int ctl = (int)((sizeof(BlockCtl) + 127) & ~(size_t)127);
-    int smem = g_smem_bytes.load();
-    if (smem < ctl + 1024) smem = ctl + 1024;
-    k.win_floats = (smem - ctl) / 4;
-    return smem;
+    const int warps = threads / 32;
+    if (!bwd) {
+        k.strip_cols = g_strip_cols.load();
+        return ctl + warps * k.strip_cols * 512;
+    }
+    const int ttab = (int)((sizeof(TTab) + 127) & ~(size_t)127);
+    k.strip_cols = sum_pw > 0 ? sum_pw : 1;
+    return ctl + p->n_heads * 2 * ttab + warps * k.strip_cols * 512;
 }
 
 template <typename Kern>
@@ -173,19 +183,20 @@ uint64_t rpool_launch_count(void) { return g_launches.load(); }
 int rpool_set_tuning(const char *key, int value)
 {
     if (!key) return fail(RPOOL_ERR_INVALID, "key is NULL");
-    if (!strcmp(key, "smem_bytes")) {
-        if (value < 8 * 1024 || value > 227 * 1024)
-            return fail(RPOOL_ERR_INVALID, "smem_bytes=%d outside [8K,227K]", value);
-        g_smem_bytes = value;
+    if (!strcmp(key, "strip_cols")) {
+        if (value < kNT || value > 64)
+            return fail(RPOOL_ERR_INVALID, "strip_cols=%d outside [%d,64]", value, kNT);
+        g_strip_cols = value;
     } else if (!strcmp(key, "threads")) {
-        if (value < 32 || value > 512 || value % 32)
-            return fail(RPOOL_ERR_INVALID, "threads=%d must be a multiple of 32 in [32,512]", value);
+        if (value < 32 || value > kMaxThreads || value % 32)
+            return fail(RPOOL_ERR_INVALID, "threads=%d must be a multiple of 32 in [32,%d]", value,
+                        kMaxThreads);
         g_threads = value;
     } else if (!strcmp(key, "order")) {
         if (value < 0 || value > 2) return fail(RPOOL_ERR_INVALID, "order=%d outside [0,2]", value);
         g_order = value;
     } else if (!strcmp(key, "force_path")) {
-        if (value < 0 || value > 3) return fail(RPOOL_ERR_INVALID, "force_path=%d outside [0,3]", value);
+        if (value < 0 || value > 2) return fail(RPOOL_ERR_INVALID, "force_path=%d outside [0,2]", value);
         g_force_path = value;
     } else {
         return fail(RPOOL_ERR_INVALID, "unknown tuning key '%s'", key);
@@ -196,7 +207,7 @@ int rpool_set_tuning(const char *key, int value)
 int rpool_get_tuning(const char *key, int *value)
 {
     if (!key || !value) return fail(RPOOL_ERR_INVALID, "NULL argument");
-    if (!strcmp(key, "smem_bytes")) *value = g_smem_bytes;
+    if (!strcmp(key, "strip_cols")) *value = g_strip_cols;
     else if (!strcmp(key, "threads")) *value = g_threads;
     else if (!strcmp(key, "order")) *value = g_order;
     else if (!strcmp(key, "force_path")) *value = g_force_path;
@@ -293,10 +304,14 @@ int rpool_forward(const rpool_problem *p, void *ws, size_t ws_size, void *stream
     if (rc) return rc;
     if (p->n_rois == 0) return RPOOL_OK;
     KParams k;
-    const int smem = fill_params(p, ws_split(ws, p->n_rois), k);
+    const int threads = g_threads.load();
+    const int smem = fill_params(p, ws_split(ws, p->n_rois), false, threads, k);
+    if (smem > kMaxSmem)
+        return fail(RPOOL_ERR_UNSUPPORTED, "forward needs %d bytes of shared memory (threads=%d, "
+                    "strip_cols=%d); the limit is %d", smem, threads, k.strip_cols, kMaxSmem);
     rc = set_smem(rpool_forward_kernel, smem);
     if (rc) return rc;
-    rpool_forward_kernel<<<p->n_rois, g_threads.load(), smem, static_cast<cudaStream_t>(stream)>>>(k);
+    rpool_forward_kernel<<<p->n_rois, threads, smem, static_cast<cudaStream_t>(stream)>>>(k);
     CUDA_TRY(cudaGetLastError(), "rpool_forward_kernel launch");
     g_launches++;
     return RPOOL_OK;
@@ -330,10 +345,15 @@ int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *strea
     }
     if (p->n_rois == 0) return RPOOL_OK;
     KParams k;
-    const int smem = fill_params(p, ws_split(ws, p->n_rois), k);
+    int threads = g_threads.load();
+    int smem = fill_params(p, ws_split(ws, p->n_rois), true, threads, k);
+    while (smem > kMaxSmem && threads > 32) {  // two wide heads: fewer warps, same result
+        threads -= 32;
+        smem = fill_params(p, ws_split(ws, p->n_rois), true, threads, k);
+    }
     rc = set_smem(rpool_backward_kernel, smem);
     if (rc) return rc;
-    rpool_backward_kernel<<<p->n_rois, g_threads.load(), smem, st>>>(k);
+    rpool_backward_kernel<<<p->n_rois, threads, smem, st>>>(k);
     CUDA_TRY(cudaGetLastError(), "rpool_backward_kernel launch");
     g_launches++;
     return RPOOL_OK;

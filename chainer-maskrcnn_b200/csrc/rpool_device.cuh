@@ -13,12 +13,15 @@
 
 namespace rpool {
 
-constexpr int kNT = 4;        // footprint width kept per bin and axis on the fast path
-constexpr int kPMax = 32;     // largest pooled extent served by the fast path
+constexpr int kNT = 4;        // footprint width kept per bin and axis on the table path
+constexpr int kPMax = 32;     // largest pooled extent served by the table path (forward)
+constexpr int kPBwd = 16;     // ... by the table path of the backward kernel
+constexpr int kExt = 64;      // largest window extent (cells per axis) of the backward table path
+constexpr int kMaxThreads = 256;  // CTA size the pooling kernels are compiled for
 constexpr int kMaxHeads = RPOOL_MAX_HEADS;
 constexpr int kMaxLevels = RPOOL_MAX_LEVELS;
 
-enum Path : int { kPathAuto = 0, kPathGeneric = 1, kPathDirect = 2, kPathStaged = 3 };
+enum Path : int { kPathAuto = 0, kPathGeneric = 1, kPathTable = 2 };
 
 struct LevelDev {
     float *data;
@@ -41,7 +44,7 @@ struct KParams {
     float *pooled[kMaxHeads];
     int S;
     int mode;
-    int win_floats;  // capacity of the staged window, in floats
+    int strip_cols;  // capacity of a warp's strip, in 512-byte columns
     int force_path;
 };
 
@@ -173,9 +176,9 @@ struct AxisTab {
 struct BlockCtl {
     AxisTab tab[kMaxHeads][2];  // [head][0 = y, 1 = x]
     int wmin[2], wmax[2];       // window extent over all heads: [0] rows, [1] cols
+    int nmax[kMaxHeads][2];     // widest footprint of any bin, per head and axis
     int eligible;
     int pad_;
-    unsigned long long mbar;
 };
 
 // Fills entry p of `t`; returns false when the footprint does not fit kNT cells.

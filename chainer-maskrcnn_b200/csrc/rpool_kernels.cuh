@@ -1,25 +1,21 @@
 // rpool_kernels.cuh -- the fused multi-level RoIAlign kernels (sm_100a).
 //
 // One CTA per RoI, scheduled through the plan's (image, level) binning.  A CTA
-//   1. decodes its RoI and level, builds per-axis footprint tables in shared
-//      memory (merged bilinear taps per bin, separable in y and x);
+//   1. decodes its RoI and level and builds per-axis footprint tables in shared
+//      memory: per bin the merged bilinear taps of its S samples (a dense run of
+//      at most kNT cells and their summed weights) -- the interpolation is
+//      separable, out = WY * X * WX^T;
 //   2. picks a path:
-//        staged  -- the RoI's feature window (all channels) is copied into
-//                   shared memory with cp.async.bulk (one bulk copy per window
-//                   row, completion on an mbarrier), in bands of bin rows when
-//                   the whole window does not fit;
-//        direct  -- same arithmetic straight from global memory (window wider
-//                   than the staging buffer);
+//        table   -- channels-last tensors, C % 4 == 0: warps take independent
+//                   (row, 128-channel slab) tasks, a lane owns 4 channels and
+//                   moves them with 128-bit accesses; the y-interpolated row
+//                   lives in a per-warp strip of shared memory, so both passes
+//                   are branch-free gathers (see the two kernels below);
 //        generic -- any layout / sampling grid / pooled size, tap by tap, in
-//                   the reference's own operation order;
-//   3. forward: every warp takes (head, bin row, 128-channel slab) tasks; a
-//      lane owns 4 channels (128-bit loads), interpolates along y once per
-//      window column, slides a kNT-column register window along x and streams
-//      the bins out with evict-first 128-bit stores;
-//      backward: every warp owns a 32-channel slab of the CTA's private
-//      gradient window in shared memory (no shared-memory atomics), walks all
-//      bins of all heads, and the CTA flushes the window once with 128-bit
-//      vector reductions (red.global.add.v4.f32) into the dense gradient.
+//                   the reference's own operation order (bit-equal forward).
+//   Forward streams the bins out with evict-first 128-bit stores; backward is
+//   the adjoint written as a gather per window cell, so the only atomics are one
+//   128-bit vector reduction (red.global.add.v4.f32) per window cell and RoI.
 #pragma once
 #include "rpool_device.cuh"
 
@@ -67,6 +63,7 @@ __device__ __forceinline__ void build_tables(const KParams &P, const RoiCtx &c, 
         ctl->wmin[0] = ctl->wmin[1] = 0x7fffffff;
         ctl->wmax[0] = ctl->wmax[1] = -1;
         ctl->eligible = 1;
+        for (int h = 0; h < kMaxHeads; ++h) ctl->nmax[h][0] = ctl->nmax[h][1] = 0;
     }
     __syncthreads();
     // entry e -> (head, axis, bin)
@@ -84,6 +81,7 @@ __device__ __forceinline__ void build_tables(const KParams &P, const RoiCtx &c, 
             if (hi >= lo) {
                 atomicMin(&ctl->wmin[axis], lo);
                 atomicMax(&ctl->wmax[axis], hi);
+                atomicMax(&ctl->nmax[h][axis], hi - lo + 1);
             }
         }
         base += ny + nx;
@@ -223,151 +221,80 @@ __device__ void generic_backward(const KParams &P, const RoiCtx &c)
 }
 
 // ---------------------------------------------------------------------------
-// window bookkeeping shared by forward and backward
+// table path, forward
 // ---------------------------------------------------------------------------
-struct Window {
-    int y0, y1, x0, x1;  // inclusive extents of the rows/cols held
-    int row_stride;      // floats between consecutive window rows
-};
-
-// Largest p1 such that bin rows [p0, p1) of table t stay within `cap` window rows.
-__device__ __forceinline__ int band_end(const AxisTab &t, int P, int p0, int cap, int &ya, int &yb)
+// Task = (head, bin row ph, 128-channel slab), one warp each; a lane owns 4
+// channels.  Per task:
+//   column pass  V[x] = sum_j wy[j] * X[ylo + j][x]   for the columns the row's
+//                bins touch, 128-bit loads through L1 (a window row is re-read
+//                by the ~5 bin rows whose footprint contains it), written to the
+//                warp's private strip in shared memory;
+//   bin pass     out[pw] = sum_k wx[pw][k] * V[lo[pw] + k], strip reads at
+//                data-dependent columns, evict-first 128-bit stores.
+// Rows wider than the strip are processed in chunks of bins.
+template <int NY>
+__device__ __forceinline__ void fwd_col_pass(const float *__restrict__ src, int row_stride, int C,
+                                             int count, int total, float4 wy, uint32_t strip,
+                                             bool active)
 {
-    int a = 0x7fffffff, b = -1, p = p0;
-    for (; p < P; ++p) {
-        const int n = t.n[p];
-        if (n == 0) continue;
-        const int lo = t.lo[p], hi = lo + n - 1;
-        const int na = lo < a ? lo : a, nb = hi > b ? hi : b;
-        if (nb - na + 1 > cap && b >= 0) break;
-        a = na;
-        b = nb;
+    // src -> (ylo, first column, lane's channels)
+    constexpr int U = NY <= 2 ? 4 : 2;  // columns in flight: at most 8 independent 128-bit loads
+    for (int i = 0; i < count; i += U) {
+        float4 t[U][NY];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int j = 0; j < NY; ++j) {
+                t[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (active && i + u < count) t[u][j] = ldg_nc128(src + (size_t)(i + u) * C + (size_t)j * row_stride);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i + u < count) {
+                float4 v;
+                v.x = wy.x * t[u][0].x; v.y = wy.x * t[u][0].y; v.z = wy.x * t[u][0].z; v.w = wy.x * t[u][0].w;
+                if (NY > 1) { v.x = fmaf(wy.y, t[u][1].x, v.x); v.y = fmaf(wy.y, t[u][1].y, v.y);
+                              v.z = fmaf(wy.y, t[u][1].z, v.z); v.w = fmaf(wy.y, t[u][1].w, v.w); }
+                if (NY > 2) { v.x = fmaf(wy.z, t[u][2].x, v.x); v.y = fmaf(wy.z, t[u][2].y, v.y);
+                              v.z = fmaf(wy.z, t[u][2].z, v.z); v.w = fmaf(wy.z, t[u][2].w, v.w); }
+                if (NY > 3) { v.x = fmaf(wy.w, t[u][3].x, v.x); v.y = fmaf(wy.w, t[u][3].y, v.y);
+                              v.z = fmaf(wy.w, t[u][3].z, v.z); v.w = fmaf(wy.w, t[u][3].w, v.w); }
+                sts128(strip + (uint32_t)(i + u) * 512u, v);
+            }
+        }
     }
-    ya = a;
-    yb = b;
-    return p;
+    // columns past the window that a zero-weight tap may still address
+    for (int i = count < 0 ? 0 : count; i < total; ++i)
+        sts128(strip + (uint32_t)i * 512u, make_float4(0.f, 0.f, 0.f, 0.f));
 }
 
-// ---------------------------------------------------------------------------
-// forward
-// ---------------------------------------------------------------------------
-template <bool kSmem>
-__device__ __forceinline__ float4 win_ld(uint32_t win_s, const float *win_g, int off)
+template <int NX>
+__device__ __forceinline__ void fwd_bin_pass(const AxisTab &xt, int pa, int pb, int lo_a, int C,
+                                             uint32_t strip, float *__restrict__ out, bool active)
 {
-    if (kSmem) return lds128(win_s + (uint32_t)off * 4u);
-    return ldg_nc128(win_g + off);
-}
-
-// One (bin row, 4 channels per lane) task.  `base` is the float offset of
-// (row ylo, col win.x0, channel c) from the window origin.
-template <bool kSmem>
-__device__ __forceinline__ void fwd_row(uint32_t win_s, const float *win_g, const Window &win,
-                                        int C, int c, int ylo, int ny, float4 wy,
-                                        const AxisTab &xt, int PW, float *__restrict__ out)
-{
-    const int base = (ylo - win.y0) * win.row_stride + c;
-    auto col = [&](int x) -> float4 {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (x >= win.x0 && x <= win.x1) {
-            const int off = base + (x - win.x0) * C;
-            float4 t = win_ld<kSmem>(win_s, win_g, off);
-            v.x = wy.x * t.x; v.y = wy.x * t.y; v.z = wy.x * t.z; v.w = wy.x * t.w;
-            if (ny > 1) {
-                t = win_ld<kSmem>(win_s, win_g, off + win.row_stride);
-                v.x = fmaf(wy.y, t.x, v.x); v.y = fmaf(wy.y, t.y, v.y);
-                v.z = fmaf(wy.y, t.z, v.z); v.w = fmaf(wy.y, t.w, v.w);
-            }
-            if (ny > 2) {
-                t = win_ld<kSmem>(win_s, win_g, off + 2 * win.row_stride);
-                v.x = fmaf(wy.z, t.x, v.x); v.y = fmaf(wy.z, t.y, v.y);
-                v.z = fmaf(wy.z, t.z, v.z); v.w = fmaf(wy.z, t.w, v.w);
-            }
-            if (ny > 3) {
-                t = win_ld<kSmem>(win_s, win_g, off + 3 * win.row_stride);
-                v.x = fmaf(wy.w, t.x, v.x); v.y = fmaf(wy.w, t.y, v.y);
-                v.z = fmaf(wy.w, t.z, v.z); v.w = fmaf(wy.w, t.w, v.w);
-            }
-        }
-        return v;
-    };
-    int xb = xt.lo[0];
-    float4 V0 = col(xb), V1 = col(xb + 1), V2 = col(xb + 2), V3 = col(xb + 3);
-    for (int pw = 0; pw < PW; ++pw) {
-        const int xl = xt.lo[pw];
-        if (xl - xb >= kNT) {
-            xb = xl;
-            V0 = col(xb); V1 = col(xb + 1); V2 = col(xb + 2); V3 = col(xb + 3);
-        } else {
-            while (xb < xl) {
-                V0 = V1; V1 = V2; V2 = V3;
-                V3 = col(xb + kNT);
-                ++xb;
-            }
-        }
+#pragma unroll 2
+    for (int pw = pa; pw < pb; ++pw) {
+        const uint32_t a = strip + (uint32_t)(xt.lo[pw] - lo_a) * 512u;
         const float4 w = xt.w[pw];
-        float4 o;
-        o.x = fmaf(w.w, V3.x, fmaf(w.z, V2.x, fmaf(w.y, V1.x, w.x * V0.x)));
-        o.y = fmaf(w.w, V3.y, fmaf(w.z, V2.y, fmaf(w.y, V1.y, w.x * V0.y)));
-        o.z = fmaf(w.w, V3.z, fmaf(w.z, V2.z, fmaf(w.y, V1.z, w.x * V0.z)));
-        o.w = fmaf(w.w, V3.w, fmaf(w.z, V2.w, fmaf(w.y, V1.w, w.x * V0.w)));
-        stg_stream128(out + (size_t)pw * C, o);
+        float4 v = lds128(a), o;
+        o.x = w.x * v.x; o.y = w.x * v.y; o.z = w.x * v.z; o.w = w.x * v.w;
+        if (NX > 1) { v = lds128(a + 512u);
+                      o.x = fmaf(w.y, v.x, o.x); o.y = fmaf(w.y, v.y, o.y); o.z = fmaf(w.y, v.z, o.z); o.w = fmaf(w.y, v.w, o.w); }
+        if (NX > 2) { v = lds128(a + 1024u);
+                      o.x = fmaf(w.z, v.x, o.x); o.y = fmaf(w.z, v.y, o.y); o.z = fmaf(w.z, v.z, o.z); o.w = fmaf(w.z, v.w, o.w); }
+        if (NX > 3) { v = lds128(a + 1536u);
+                      o.x = fmaf(w.w, v.x, o.x); o.y = fmaf(w.w, v.y, o.y); o.z = fmaf(w.w, v.z, o.z); o.w = fmaf(w.w, v.w, o.w); }
+        if (active) stg_stream128(out + (size_t)pw * C, o);
     }
 }
 
-// All (bin row in [p0,p1), slab) tasks of head h against the current window.
-template <bool kSmem>
-__device__ __forceinline__ void fwd_tasks(const KParams &P, const RoiCtx &c, const BlockCtl *ctl,
-                                          uint32_t win_s, const float *win_g, const Window &win,
-                                          int h, int p0, int p1)
-{
-    const int C = P.C;
-    const int slabs = (C + 127) >> 7;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int PH = P.PH[h], PW = P.PW[h];
-    const AxisTab &yt = ctl->tab[h][0];
-    const AxisTab &xt = ctl->tab[h][1];
-    const int ntask = (p1 - p0) * slabs;
-    for (int t = warp; t < ntask; t += nwarps) {
-        const int ph = p0 + t / slabs;
-        const int ch = (t % slabs) * 128 + lane * 4;
-        if (ch >= C) continue;
-        float *out = P.pooled[h] + (((size_t)c.r * PH + ph) * PW) * C + ch;
-        const int ny = yt.n[ph];
-        if (ny == 0) {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int pw = 0; pw < PW; ++pw) stg_stream128(out + (size_t)pw * C, z);
-            continue;
-        }
-        fwd_row<kSmem>(win_s, win_g, win, C, ch, yt.lo[ph], ny, yt.w[ph], xt, PW, out);
-    }
-}
-
-// Copies window rows [ya, yb] x cols [x0, x1] (all channels) of image b into
-// shared memory: one bulk async copy per row, completion counted on the mbarrier.
-__device__ __forceinline__ void stage_window(const RoiCtx &c, int C, BlockCtl *ctl, uint32_t win_s,
-                                             int ya, int yb, int x0, int x1, unsigned &phase)
-{
-    const int nrows = yb - ya + 1;
-    const unsigned row_bytes = (unsigned)(x1 - x0 + 1) * C * 4u;
-    if (threadIdx.x < 32) {
-        if (threadIdx.x == 0) mbar_expect_tx(&ctl->mbar, row_bytes * nrows);
-        __syncwarp();
-        for (int i = threadIdx.x; i < nrows; i += 32) {
-            const float *src = c.L.data + (((size_t)c.b * c.L.H + (ya + i)) * c.L.W + x0) * C;
-            bulk_g2s(win_s + (uint32_t)i * row_bytes, src, row_bytes, &ctl->mbar);
-        }
-    }
-    mbar_wait(&ctl->mbar, phase);
-    phase ^= 1u;
-}
-
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(kMaxThreads, 3)
 rpool_forward_kernel(const __grid_constant__ KParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockCtl *ctl = reinterpret_cast<BlockCtl *>(smem_raw);
     constexpr int kCtlBytes = (sizeof(BlockCtl) + 127) & ~127;
-    const uint32_t win_s = smem_u32(smem_raw + kCtlBytes);
 
     RoiCtx c;
     roi_prologue(P, false, c);
@@ -375,253 +302,228 @@ rpool_forward_kernel(const __grid_constant__ KParams P)
         generic_forward(P, c);
         return;
     }
-    if (threadIdx.x == 0) {
-        mbar_init(&ctl->mbar, 1);
-        fence_mbar_init();
-    }
     build_tables(P, c, ctl);
     if (!ctl->eligible) {
         generic_forward(P, c);
         return;
     }
     const int C = P.C;
-    const int x0 = ctl->wmin[1], x1 = ctl->wmax[1];
-    const int y0 = ctl->wmin[0], y1 = ctl->wmax[0];
-    if (x1 < x0 || y1 < y0) {
-        // no valid sample anywhere: all outputs are zero
-        for (int h = 0; h < P.n_heads; ++h) {
-            const int total = P.PH[h] * P.PW[h] * C;
-            float *out = P.pooled[h] + (size_t)c.r * total;
-            for (int i = threadIdx.x; i < total; i += blockDim.x) out[i] = 0.f;
-        }
-        return;
-    }
-    const int Wc = x1 - x0 + 1;
-    const int row_floats = Wc * C;
-    const int cap_rows = P.win_floats / row_floats;
-    int path = P.force_path;
-    if (path == kPathAuto) path = (cap_rows >= kNT) ? kPathStaged : kPathDirect;
-    if (path == kPathStaged && cap_rows < kNT) path = kPathDirect;
-
-    if (path == kPathDirect) {
-        Window w{0, c.L.H - 1, 0, c.L.W - 1, c.L.W * C};
-        const float *img = c.L.data + (size_t)c.b * c.L.H * c.L.W * C;
-        for (int h = 0; h < P.n_heads; ++h)
-            fwd_tasks<false>(P, c, ctl, 0, img, w, h, 0, P.PH[h]);
-        return;
-    }
-
-    unsigned phase = 0;
-    if (y1 - y0 + 1 <= cap_rows) {
-        stage_window(c, C, ctl, win_s, y0, y1, x0, x1, phase);
-        Window w{y0, y1, x0, x1, row_floats};
-        for (int h = 0; h < P.n_heads; ++h)
-            fwd_tasks<true>(P, c, ctl, win_s, nullptr, w, h, 0, P.PH[h]);
-        return;
-    }
-    for (int h = 0; h < P.n_heads; ++h) {
-        int p0 = 0;
-        while (p0 < P.PH[h]) {
-            int ya, yb;
-            const int p1 = band_end(ctl->tab[h][0], P.PH[h], p0, cap_rows, ya, yb);
-            if (yb >= ya) {
-                stage_window(c, C, ctl, win_s, ya, yb, x0, x1, phase);
-                Window w{ya, yb, x0, x1, row_floats};
-                fwd_tasks<true>(P, c, ctl, win_s, nullptr, w, h, p0, p1);
-                __syncthreads();  // all reads of this band done before it is overwritten
-            } else {
-                Window w{0, -1, x0, x1, row_floats};
-                fwd_tasks<true>(P, c, ctl, win_s, nullptr, w, h, p0, p1);
-            }
-            p0 = p1;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
-// backward
-// ---------------------------------------------------------------------------
-// Adds a*wy[j] to window cells (ylo+j, x), j < ny, for this lane's channel.
-template <bool kSmem>
-__device__ __forceinline__ void bwd_retire(uint32_t win_s, float *win_g, const Window &win, int C,
-                                           int base, int ny, float4 wy, float a, int x)
-{
-    if (x < win.x0 || x > win.x1) return;
-    const int off = base + (x - win.x0) * C;
-    const float wv[4] = {wy.x, wy.y, wy.z, wy.w};
-#pragma unroll
-    for (int j = 0; j < kNT; ++j) {
-        if (j < ny) {
-            const int o = off + j * win.row_stride;
-            if (kSmem) {
-                const uint32_t a32 = win_s + (uint32_t)o * 4u;
-                sts32(a32, fmaf(wv[j], a, lds32(a32)));
-            } else {
-                red_add_f32(win_g + o, wv[j] * a);
-            }
-        }
-    }
-}
-
-// One bin row for one channel per lane: gy values are pushed through the x
-// footprints into a sliding set of kNT column accumulators; a column that
-// slides out is multiplied by the row's y weights and added to the window.
-template <bool kSmem>
-__device__ __forceinline__ void bwd_row(uint32_t win_s, float *win_g, const Window &win, int C,
-                                        int c, int ylo, int ny, float4 wy, const AxisTab &xt,
-                                        int PW, const float *__restrict__ gy)
-{
-    const int base = (ylo - win.y0) * win.row_stride + c;
-    float A0 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f;
-    int xb = xt.lo[0];
-    for (int pw0 = 0; pw0 < PW; pw0 += 8) {
-        float g[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            g[k] = (pw0 + k < PW) ? ldg_stream32(gy + (size_t)(pw0 + k) * C) : 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int pw = pw0 + k;
-            if (pw < PW) {
-                const int xl = xt.lo[pw];
-                if (xl - xb >= kNT) {
-                    bwd_retire<kSmem>(win_s, win_g, win, C, base, ny, wy, A0, xb);
-                    bwd_retire<kSmem>(win_s, win_g, win, C, base, ny, wy, A1, xb + 1);
-                    bwd_retire<kSmem>(win_s, win_g, win, C, base, ny, wy, A2, xb + 2);
-                    bwd_retire<kSmem>(win_s, win_g, win, C, base, ny, wy, A3, xb + 3);
-                    A0 = A1 = A2 = A3 = 0.f;
-                    xb = xl;
-                } else {
-                    while (xb < xl) {
-                        bwd_retire<kSmem>(win_s, win_g, win, C, base, ny, wy, A0, xb);
-                        A0 = A1; A1 = A2; A2 = A3; A3 = 0.f;
-                        ++xb;
-                    }
-                }
-                const float4 w = xt.w[pw];
-                A0 = fmaf(w.x, g[k], A0);
-                A1 = fmaf(w.y, g[k], A1);
-                A2 = fmaf(w.z, g[k], A2);
-                A3 = fmaf(w.w, g[k], A3);
-            }
-        }
-    }
-    bwd_retire<kSmem>(win_s, win_g, win, C, base, ny, wy, A0, xb);
-    bwd_retire<kSmem>(win_s, win_g, win, C, base, ny, wy, A1, xb + 1);
-    bwd_retire<kSmem>(win_s, win_g, win, C, base, ny, wy, A2, xb + 2);
-    bwd_retire<kSmem>(win_s, win_g, win, C, base, ny, wy, A3, xb + 3);
-}
-
-// Every warp owns 32-channel slabs; within a slab it walks rows [p0,p1) of head h.
-template <bool kSmem>
-__device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, const BlockCtl *ctl,
-                                          uint32_t win_s, float *win_g, const Window &win,
-                                          int h, int p0, int p1)
-{
-    const int C = P.C;
-    const int slabs = (C + 31) >> 5;
+    const int wx1 = ctl->wmax[1];
+    const int slabs = (C + 127) >> 7;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int PH = P.PH[h], PW = P.PW[h];
-    const AxisTab &yt = ctl->tab[h][0];
-    const AxisTab &xt = ctl->tab[h][1];
-    for (int s = warp; s < slabs; s += nwarps) {
-        const int ch = s * 32 + lane;
-        if (ch >= C) continue;
-        for (int ph = p0; ph < p1; ++ph) {
-            const int ny = yt.n[ph];
-            if (ny == 0) continue;
-            const float *gy = P.pooled[h] + (((size_t)c.r * PH + ph) * PW) * C + ch;
-            bwd_row<kSmem>(win_s, win_g, win, C, ch, yt.lo[ph], ny, yt.w[ph], xt, PW, gy);
+    const uint32_t strip = smem_u32(smem_raw + kCtlBytes) + (uint32_t)warp * (uint32_t)P.strip_cols * 512u +
+                           (uint32_t)lane * 16u;
+    const int SC = P.strip_cols;
+    const int row_stride = c.L.W * C;
+    const float *img = c.L.data + (size_t)c.b * c.L.H * row_stride;
+
+    int ntask = 0;
+    for (int h = 0; h < P.n_heads; ++h) ntask += P.PH[h] * slabs;
+    for (int t = warp; t < ntask; t += nwarps) {
+        int h = 0, tt = t;
+        while (tt >= P.PH[h] * slabs) { tt -= P.PH[h] * slabs; ++h; }
+        const int ph = tt / slabs;
+        const int ch = (tt - ph * slabs) * 128 + lane * 4;
+        const bool active = ch < C;
+        const int PH = P.PH[h], PW = P.PW[h];
+        const AxisTab &yt = ctl->tab[h][0];
+        const AxisTab &xt = ctl->tab[h][1];
+        float *out = P.pooled[h] + (((size_t)c.r * PH + ph) * PW) * C + ch;
+        const int ny = yt.n[ph];
+        const int NX = ctl->nmax[h][1];
+        if (ny == 0 || NX == 0) {
+            if (active)
+                for (int pw = 0; pw < PW; ++pw) stg_stream128(out + (size_t)pw * C, make_float4(0.f, 0.f, 0.f, 0.f));
+            continue;
+        }
+        const float4 wy = yt.w[ph];
+        const float *rowp = img + (size_t)yt.lo[ph] * row_stride + ch;
+        int pa = 0;
+        while (pa < PW) {
+            const int lo_a = xt.lo[pa];
+            int pb = pa + 1;
+            while (pb < PW && xt.lo[pb] + NX - lo_a <= SC) ++pb;
+            const int last = xt.lo[pb - 1] + NX - 1;          // last strip column any tap addresses
+            const int total = last - lo_a + 1;
+            const int count = (last < wx1 ? last : wx1) - lo_a + 1;  // columns that exist in the window
+            const float *src = rowp + (size_t)lo_a * C;
+            switch (ny) {
+            case 1: fwd_col_pass<1>(src, row_stride, C, count, total, wy, strip, active); break;
+            case 2: fwd_col_pass<2>(src, row_stride, C, count, total, wy, strip, active); break;
+            case 3: fwd_col_pass<3>(src, row_stride, C, count, total, wy, strip, active); break;
+            default: fwd_col_pass<4>(src, row_stride, C, count, total, wy, strip, active); break;
+            }
+            __syncwarp();
+            switch (NX) {
+            case 1: fwd_bin_pass<1>(xt, pa, pb, lo_a, C, strip, out, active); break;
+            case 2: fwd_bin_pass<2>(xt, pa, pb, lo_a, C, strip, out, active); break;
+            case 3: fwd_bin_pass<3>(xt, pa, pb, lo_a, C, strip, out, active); break;
+            default: fwd_bin_pass<4>(xt, pa, pb, lo_a, C, strip, out, active); break;
+            }
+            __syncwarp();
+            pa = pb;
         }
     }
 }
 
-__device__ __forceinline__ void zero_window(uint32_t win_s, int nfloats)
-{
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = threadIdx.x * 4; i < nfloats; i += blockDim.x * 4) sts128(win_s + (uint32_t)i * 4u, z);
-}
+// ---------------------------------------------------------------------------
+// table path, backward
+// ---------------------------------------------------------------------------
+// The adjoint as a gather, so that no two warps ever add to the same place:
+// task = (window row y, 128-channel slab), one warp each.  Per task:
+//   row pass     Z[pw] = sum over bin rows ph covering y of wyT[y][ph] * gy[ph][pw]
+//                (128-bit loads, every load independent), written to the warp's strip;
+//   column pass  G[x] = sum over bins pw covering x of wxT[x][pw] * Z[pw];
+//                one 128-bit vector reduction per window cell into the dense gradient.
+// The transposed weight tables (dense, kExt x kPBwd per axis) are built in
+// shared memory from the forward footprint tables.
+struct TTab {
+    float w[kExt][kPBwd];
+    int pa[kExt], pb[kExt];  // covering bins of row/column i: [pa, pb)
+};
 
-// Adds the private window into the dense gradient with 128-bit reductions.
-__device__ __forceinline__ void flush_window(const RoiCtx &c, int C, uint32_t win_s, int ya, int yb,
-                                             int x0, int x1)
+__device__ __forceinline__ void build_ttabs(const KParams &P, const BlockCtl *ctl, TTab *tt)
 {
-    const int row4 = (x1 - x0 + 1) * C / 4;
-    const int total4 = (yb - ya + 1) * row4;
-    for (int i = threadIdx.x; i < total4; i += blockDim.x) {
-        const float4 v = lds128(win_s + (uint32_t)i * 16u);
-        if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
-        const int row = i / row4, rem = i - row * row4;
-        float *dst = c.L.data + (((size_t)c.b * c.L.H + (ya + row)) * c.L.W + x0) * C + (size_t)rem * 4;
-        red_add_v4(dst, v);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int ntab = P.n_heads * 2;
+    for (int a = 0; a < ntab; ++a) {
+        const int ext = ctl->wmax[a & 1] - ctl->wmin[a & 1] + 1;
+        float *w = &tt[a].w[0][0];
+        for (int i = tid; i < ext * kPBwd; i += nt) w[i] = 0.f;
+        for (int i = tid; i < ext; i += nt) { tt[a].pa[i] = 0x7fffffff; tt[a].pb[i] = 0; }
     }
+    __syncthreads();
+    int base = 0;
+    for (int h = 0; h < P.n_heads; ++h) {
+        const int ny = P.PH[h], nx = P.PW[h];
+        const int e = tid - base;
+        if (e >= 0 && e < ny + nx) {
+            const int axis = e < ny ? 0 : 1;
+            const int p = axis ? e - ny : e;
+            const AxisTab &t = ctl->tab[h][axis];
+            TTab &T = tt[h * 2 + axis];
+            const int n = t.n[p], row0 = t.lo[p] - ctl->wmin[axis];
+            const float4 w4 = t.w[p];
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int k = 0; k < kNT; ++k) {
+                if (k < n) {
+                    T.w[row0 + k][p] = wv[k];
+                    atomicMin(&T.pa[row0 + k], p);
+                    atomicMax(&T.pb[row0 + k], p + 1);
+                }
+            }
+        }
+        base += ny + nx;
+    }
+    __syncthreads();
 }
 
-__global__ void __launch_bounds__(512)
+constexpr int kZ = 7;  // bins per register chunk of the row pass
+
+__global__ void __launch_bounds__(kMaxThreads, 3)
 rpool_backward_kernel(const __grid_constant__ KParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockCtl *ctl = reinterpret_cast<BlockCtl *>(smem_raw);
     constexpr int kCtlBytes = (sizeof(BlockCtl) + 127) & ~127;
-    const uint32_t win_s = smem_u32(smem_raw + kCtlBytes);
+    constexpr int kTTabBytes = (sizeof(TTab) + 127) & ~127;
+    TTab *tt = reinterpret_cast<TTab *>(smem_raw + kCtlBytes);
 
     RoiCtx c;
     roi_prologue(P, true, c);
     if (!c.valid) return;
-    if (!c.fast_ok) {
+    bool table_ok = c.fast_ok;
+    for (int h = 0; h < P.n_heads; ++h) table_ok = table_ok && P.PH[h] <= kPBwd && P.PW[h] <= kPBwd;
+    if (!table_ok) {
         generic_backward(P, c);
         return;
     }
     build_tables(P, c, ctl);
-    if (!ctl->eligible) {
+    const int x0 = ctl->wmin[1], x1 = ctl->wmax[1];
+    const int y0 = ctl->wmin[0], y1 = ctl->wmax[0];
+    if (!ctl->eligible || x1 - x0 >= kExt || y1 - y0 >= kExt) {
         generic_backward(P, c);
         return;
     }
-    const int C = P.C;
-    const int x0 = ctl->wmin[1], x1 = ctl->wmax[1];
-    const int y0 = ctl->wmin[0], y1 = ctl->wmax[0];
     if (x1 < x0 || y1 < y0) return;
-    const int Wc = x1 - x0 + 1;
-    const int row_floats = Wc * C;
-    const int cap_rows = P.win_floats / row_floats;
-    int path = P.force_path;
-    if (path == kPathAuto) path = (cap_rows >= kNT) ? kPathStaged : kPathDirect;
-    if (path == kPathStaged && cap_rows < kNT) path = kPathDirect;
+    build_ttabs(P, ctl, tt);
 
-    if (path == kPathDirect) {
-        Window w{0, c.L.H - 1, 0, c.L.W - 1, c.L.W * C};
-        float *img = c.L.data + (size_t)c.b * c.L.H * c.L.W * C;
-        for (int h = 0; h < P.n_heads; ++h)
-            bwd_tasks<false>(P, c, ctl, 0, img, w, h, 0, P.PH[h]);
-        return;
-    }
+    const int C = P.C;
+    const int slabs = (C + 127) >> 7;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const uint32_t strip = smem_u32(smem_raw + kCtlBytes + P.n_heads * 2 * kTTabBytes) +
+                           (uint32_t)warp * (uint32_t)P.strip_cols * 512u + (uint32_t)lane * 16u;
+    const int Hc = y1 - y0 + 1, Wc = x1 - x0 + 1;
+    float *img = c.L.data + (size_t)c.b * c.L.H * c.L.W * C;
 
-    if (y1 - y0 + 1 <= cap_rows) {
-        zero_window(win_s, (y1 - y0 + 1) * row_floats);
-        __syncthreads();
-        Window w{y0, y1, x0, x1, row_floats};
-        for (int h = 0; h < P.n_heads; ++h)
-            bwd_tasks<true>(P, c, ctl, win_s, nullptr, w, h, 0, P.PH[h]);
-        __syncthreads();
-        flush_window(c, C, win_s, y0, y1, x0, x1);
-        return;
-    }
-    for (int h = 0; h < P.n_heads; ++h) {
-        int p0 = 0;
-        while (p0 < P.PH[h]) {
-            int ya, yb;
-            const int p1 = band_end(ctl->tab[h][0], P.PH[h], p0, cap_rows, ya, yb);
-            if (yb >= ya) {
-                zero_window(win_s, (yb - ya + 1) * row_floats);
-                __syncthreads();
-                Window w{ya, yb, x0, x1, row_floats};
-                bwd_tasks<true>(P, c, ctl, win_s, nullptr, w, h, p0, p1);
-                __syncthreads();
-                flush_window(c, C, win_s, ya, yb, x0, x1);
-                __syncthreads();
+    const int ntask = Hc * slabs;
+    for (int t = warp; t < ntask; t += nwarps) {
+        const int i = t / slabs;
+        const int ch = (t - i * slabs) * 128 + lane * 4;
+        const bool active = ch < C;
+        // ---- row pass
+        unsigned hmask = 0;
+        int soff = 0;
+        for (int h = 0; h < P.n_heads; ++h) {
+            const TTab &T = tt[h * 2];
+            const int PH = P.PH[h], PW = P.PW[h];
+            const int pa = T.pa[i], pb = T.pb[i];
+            if (pa < pb) {
+                hmask |= 1u << h;
+                const float *gbase = P.pooled[h] + ((size_t)c.r * PH * PW) * C + ch;
+                for (int pw0 = 0; pw0 < PW; pw0 += kZ) {
+                    float4 Z[kZ];
+#pragma unroll
+                    for (int k = 0; k < kZ; ++k) Z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int ph = pa; ph < pb; ++ph) {
+                        const float w = T.w[i][ph];
+                        const float *g = gbase + ((size_t)ph * PW + pw0) * C;
+                        float4 v[kZ];
+#pragma unroll
+                        for (int k = 0; k < kZ; ++k) {
+                            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (active && pw0 + k < PW) v[k] = ldg_nc128(g + (size_t)k * C);
+                        }
+#pragma unroll
+                        for (int k = 0; k < kZ; ++k) {
+                            Z[k].x = fmaf(w, v[k].x, Z[k].x); Z[k].y = fmaf(w, v[k].y, Z[k].y);
+                            Z[k].z = fmaf(w, v[k].z, Z[k].z); Z[k].w = fmaf(w, v[k].w, Z[k].w);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kZ; ++k)
+                        if (pw0 + k < PW) sts128(strip + (uint32_t)(soff + pw0 + k) * 512u, Z[k]);
+                }
             }
-            p0 = p1;
+            soff += PW;
         }
+        if (hmask == 0) continue;  // a window row between footprints: nothing lands on it
+        __syncwarp();
+        // ---- column pass
+        float *grow = img + ((size_t)(y0 + i) * c.L.W + x0) * C + ch;
+        for (int j = 0; j < Wc; ++j) {
+            float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool any = false;
+            soff = 0;
+            for (int h = 0; h < P.n_heads; ++h) {
+                if (hmask & (1u << h)) {
+                    const TTab &T = tt[h * 2 + 1];
+                    const int qa = T.pa[j], qb = T.pb[j];
+                    any = any || (qa < qb);
+#pragma unroll 2
+                    for (int pw = qa; pw < qb; ++pw) {
+                        const float w = T.w[j][pw];
+                        const float4 z = lds128(strip + (uint32_t)(soff + pw) * 512u);
+                        G.x = fmaf(w, z.x, G.x); G.y = fmaf(w, z.y, G.y);
+                        G.z = fmaf(w, z.z, G.z); G.w = fmaf(w, z.w, G.w);
+                    }
+                }
+                soff += P.PW[h];
+            }
+            if (any && active) red_add_v4(grow + (size_t)j * C, G);
+        }
+        __syncwarp();
     }
 }
 

@@ -55,10 +55,10 @@ def test_thresholds_libc_equal_numpy():
 
 
 def test_tuning_roundtrip_and_errors():
-    old = _lib.get_tuning("smem_bytes")
-    _lib.set_tuning(smem_bytes=40 * 1024)
-    assert _lib.get_tuning("smem_bytes") == 40 * 1024
-    _lib.set_tuning(smem_bytes=old)
+    old = _lib.get_tuning("strip_cols")
+    _lib.set_tuning(strip_cols=9)
+    assert _lib.get_tuning("strip_cols") == 9
+    _lib.set_tuning(strip_cols=old)
     with pytest.raises(_lib.RpoolError):
         _lib.set_tuning(threads=100)
     with pytest.raises(_lib.RpoolError):

@@ -22,13 +22,12 @@ pytestmark = pytest.mark.gpu
 
 FWD_TOL = 1e-5
 BWD_TOL = 1e-4
-PATHS = {"auto": _lib.PATH_AUTO, "generic": _lib.PATH_GENERIC, "direct": _lib.PATH_DIRECT,
-         "staged": _lib.PATH_STAGED}
+PATHS = {"auto": _lib.PATH_AUTO, "generic": _lib.PATH_GENERIC, "table": _lib.PATH_TABLE}
 
 
 @pytest.fixture(autouse=True)
 def _reset_tuning():
-    defaults = {k: _lib.get_tuning(k) for k in ("smem_bytes", "threads", "order", "force_path")}
+    defaults = {k: _lib.get_tuning(k) for k in ("strip_cols", "threads", "order", "force_path")}
     yield
     _lib.set_tuning(**defaults)
 
@@ -92,7 +91,7 @@ def test_golden_reference_fixture_single_level_op(golden_dir):
     d = np.load(os.path.join(golden_dir, "reference_fixture.npz"))
     outh, outw, scale = int(d["outh"]), int(d["outw"]), float(d["scale"])
     x, rois, gy = dev(d["x"]), dev(d["rois"]), dev(d["gy"])
-    for path in ("auto", "generic", "direct"):
+    for path in ("auto", "generic", "table"):
         _lib.set_tuning(force_path=PATHS[path])
         f = ROIAlign2D(outh, outw, scale)
         (y,) = f.forward_gpu((x, rois))
@@ -160,12 +159,12 @@ def test_levels_random_million_bit_exact():
 # ---------------------------------------------------------------------------
 # seeded random cases against the oracle, every kernel path
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("path,smem_kb", [("auto", 74), ("generic", 74), ("direct", 74),
-                                          ("staged", 74), ("staged", 24), ("auto", 12)])
+@pytest.mark.parametrize("path,strip_cols", [("auto", 12), ("generic", 12), ("table", 12),
+                                             ("table", 4), ("table", 7), ("auto", 40)])
 @pytest.mark.parametrize("mode_name,S", [("chainer", 1), ("caffe2", 1), ("caffe2", 2), ("caffe2", 3)])
-def test_fused_vs_oracle(path, smem_kb, mode_name, S):
+def test_fused_vs_oracle(path, strip_cols, mode_name, S):
     rng, feats, rois, levels, scales = make_case(seed=S * 7 + len(path))
-    _lib.set_tuning(force_path=PATHS[path], smem_bytes=smem_kb * 1024)
+    _lib.set_tuning(force_path=PATHS[path], strip_cols=strip_cols)
     mode = _lib.COORD_CHAINER if mode_name == "chainer" else _lib.COORD_CAFFE2
     sizes = [7, 14]
     gys = [synth.make_gy(rng, rois.shape[0], feats[0].shape[1], P) for P in sizes]
@@ -179,7 +178,7 @@ def test_fused_vs_oracle(path, smem_kb, mode_name, S):
         assert oracle.rel_err(g, w) <= BWD_TOL
 
 
-@pytest.mark.parametrize("threads", [64, 128, 224, 512])
+@pytest.mark.parametrize("threads", [32, 64, 128, 224])
 def test_block_sizes(threads):
     rng, feats, rois, levels, scales = make_case(seed=3, C=128, per_img=60)
     _lib.set_tuning(threads=threads)
@@ -261,7 +260,7 @@ def test_edge_cases_caffe2_borders_and_degenerate():
                      [1, 10, 10, 10, 10], [0, 0, 0, 54, 40], [1, 53.9, 39.9, 54, 40],
                      [0, 25, 18, 80, 70]], np.float32)       # xy format
     gy = rng.uniform(-1, 1, (rois.shape[0], 8, 7, 7)).astype(np.float32)
-    for path in ("auto", "generic", "direct", "staged"):
+    for path in ("auto", "generic", "table"):
         _lib.set_tuning(force_path=PATHS[path])
         for S in (1, 2):
             outs, plan = _engine.forward([dev(x)], dev(rois), None, [0.5], [7], S,
