@@ -18,7 +18,7 @@ thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 
 // tuning knobs (process-wide; experiments only)
-std::atomic<int> g_strip_cols{12};
+std::atomic<int> g_prefetch{0};
 std::atomic<int> g_threads{256};
 std::atomic<int> g_order{1};
 std::atomic<int> g_force_path{kPathAuto};
@@ -151,10 +151,8 @@ int fill_params(const rpool_problem *p, const Workspace &w, bool bwd, int thread
     k.force_path = g_force_path.load();
     const int ctl = (int)((sizeof(BlockCtl) + 127) & ~(size_t)127);
     const int warps = threads / 32;
-    if (!bwd) {
-        k.strip_cols = g_strip_cols.load();
-        return ctl + warps * k.strip_cols * 512;
-    }
+    k.prefetch = g_prefetch.load();
+    if (!bwd) return ctl;
     const int ttab = (int)((sizeof(TTab) + 127) & ~(size_t)127);
     k.strip_cols = sum_pw > 0 ? sum_pw : 1;
     return ctl + p->n_heads * 2 * ttab + warps * k.strip_cols * 512;
@@ -183,10 +181,10 @@ uint64_t rpool_launch_count(void) { return g_launches.load(); }
 int rpool_set_tuning(const char *key, int value)
 {
     if (!key) return fail(RPOOL_ERR_INVALID, "key is NULL");
-    if (!strcmp(key, "strip_cols")) {
-        if (value < kNT || value > 64)
-            return fail(RPOOL_ERR_INVALID, "strip_cols=%d outside [%d,64]", value, kNT);
-        g_strip_cols = value;
+    if (!strcmp(key, "prefetch")) {
+        if (value < 0 || value > 65536)
+            return fail(RPOOL_ERR_INVALID, "prefetch=%d outside [0,65536]", value);
+        g_prefetch = value;
     } else if (!strcmp(key, "threads")) {
         if (value < 32 || value > kMaxThreads || value % 32)
             return fail(RPOOL_ERR_INVALID, "threads=%d must be a multiple of 32 in [32,%d]", value,
@@ -207,7 +205,7 @@ int rpool_set_tuning(const char *key, int value)
 int rpool_get_tuning(const char *key, int *value)
 {
     if (!key || !value) return fail(RPOOL_ERR_INVALID, "NULL argument");
-    if (!strcmp(key, "strip_cols")) *value = g_strip_cols;
+    if (!strcmp(key, "prefetch")) *value = g_prefetch;
     else if (!strcmp(key, "threads")) *value = g_threads;
     else if (!strcmp(key, "order")) *value = g_order;
     else if (!strcmp(key, "force_path")) *value = g_force_path;
@@ -307,8 +305,8 @@ int rpool_forward(const rpool_problem *p, void *ws, size_t ws_size, void *stream
     const int threads = g_threads.load();
     const int smem = fill_params(p, ws_split(ws, p->n_rois), false, threads, k);
     if (smem > kMaxSmem)
-        return fail(RPOOL_ERR_UNSUPPORTED, "forward needs %d bytes of shared memory (threads=%d, "
-                    "strip_cols=%d); the limit is %d", smem, threads, k.strip_cols, kMaxSmem);
+        return fail(RPOOL_ERR_UNSUPPORTED, "forward needs %d bytes of shared memory; the limit is %d",
+                    smem, kMaxSmem);
     rc = set_smem(rpool_forward_kernel, smem);
     if (rc) return rc;
     rpool_forward_kernel<<<p->n_rois, threads, smem, static_cast<cudaStream_t>(stream)>>>(k);

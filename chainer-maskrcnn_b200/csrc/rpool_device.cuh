@@ -44,7 +44,8 @@ struct KParams {
     float *pooled[kMaxHeads];
     int S;
     int mode;
-    int strip_cols;  // capacity of a warp's strip, in 512-byte columns
+    int strip_cols;  // backward: entries of a warp's strip (512 bytes each)
+    int prefetch;    // backward: L2 prefetch distance in CTAs (0 = off)
     int force_path;
 };
 
@@ -177,6 +178,8 @@ struct BlockCtl {
     AxisTab tab[kMaxHeads][2];  // [head][0 = y, 1 = x]
     int wmin[2], wmax[2];       // window extent over all heads: [0] rows, [1] cols
     int nmax[kMaxHeads][2];     // widest footprint of any bin, per head and axis
+    int nchunk[kMaxHeads];      // forward: bins cut into chunks of bounded x extent
+    unsigned char cstart[kMaxHeads][kPMax + 4];
     int eligible;
     int pad_;
 };
@@ -272,6 +275,12 @@ __device__ __forceinline__ void red_add_v4(float *p, float4 v)
 __device__ __forceinline__ void red_add_f32(float *p, float v)
 {
     asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+
+// bulk L2 prefetch through the TMA unit (bytes: multiple of 16)
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
 }
 
 // mbarrier + bulk async copy (the non-tensor TMA path: UBLKCP in SASS)

@@ -224,96 +224,79 @@ __device__ void generic_backward(const KParams &P, const RoiCtx &c)
 // table path, forward
 // ---------------------------------------------------------------------------
 // Task = (head, bin row ph, 128-channel slab), one warp each; a lane owns 4
-// channels.  Per task:
-//   column pass  V[x] = sum_j wy[j] * X[ylo + j][x]   for the columns the row's
-//                bins touch, 128-bit loads through L1 (a window row is re-read
-//                by the ~5 bin rows whose footprint contains it), written to the
-//                warp's private strip in shared memory;
-//   bin pass     out[pw] = sum_k wx[pw][k] * V[lo[pw] + k], strip reads at
-//                data-dependent columns, evict-first 128-bit stores.
-// Rows wider than the strip are processed in chunks of bins.
-template <int NY>
-__device__ __forceinline__ void fwd_col_pass(const float *__restrict__ src, int row_stride, int C,
-                                             int count, int total, float4 wy, uint32_t strip,
-                                             bool active)
+// channels.  The row's bins are cut into chunks whose footprints span at most
+// kSW window columns.  Per chunk:
+//   column pass  V[s] = sum_j wy[j] * X[ylo + j][lo_a + s], s < kSW, kept in
+//                registers; 128-bit loads through L1 (a window row is re-read by
+//                the ~5 bin rows whose footprint contains it), all loads of one
+//                window row in flight together;
+//   bin pass     out[pw] = sum_k wx[pw][k] * V[lo[pw] - lo_a + k]: the offset is
+//                warp-uniform, so a switch on it selects code whose register
+//                operands are static; evict-first 128-bit stores.
+// kC > 0 fixes the channel count at compile time (address arithmetic folds
+// into immediates); kC == 0 reads it from the parameters.
+constexpr int kSW = 8;
+
+__device__ __forceinline__ void fma4(float4 &a, float w, const float4 &v)
 {
-    // src -> (ylo, first column, lane's channels)
-    constexpr int U = NY <= 2 ? 4 : 2;  // columns in flight: at most 8 independent 128-bit loads
-    for (int i = 0; i < count; i += U) {
-        float4 t[U][NY];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-#pragma unroll
-            for (int j = 0; j < NY; ++j) {
-                t[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (active && i + u < count) t[u][j] = ldg_nc128(src + (size_t)(i + u) * C + (size_t)j * row_stride);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (i + u < count) {
-                float4 v;
-                v.x = wy.x * t[u][0].x; v.y = wy.x * t[u][0].y; v.z = wy.x * t[u][0].z; v.w = wy.x * t[u][0].w;
-                if (NY > 1) { v.x = fmaf(wy.y, t[u][1].x, v.x); v.y = fmaf(wy.y, t[u][1].y, v.y);
-                              v.z = fmaf(wy.y, t[u][1].z, v.z); v.w = fmaf(wy.y, t[u][1].w, v.w); }
-                if (NY > 2) { v.x = fmaf(wy.z, t[u][2].x, v.x); v.y = fmaf(wy.z, t[u][2].y, v.y);
-                              v.z = fmaf(wy.z, t[u][2].z, v.z); v.w = fmaf(wy.z, t[u][2].w, v.w); }
-                if (NY > 3) { v.x = fmaf(wy.w, t[u][3].x, v.x); v.y = fmaf(wy.w, t[u][3].y, v.y);
-                              v.z = fmaf(wy.w, t[u][3].z, v.z); v.w = fmaf(wy.w, t[u][3].w, v.w); }
-                sts128(strip + (uint32_t)(i + u) * 512u, v);
-            }
-        }
-    }
-    // columns past the window that a zero-weight tap may still address
-    for (int i = count < 0 ? 0 : count; i < total; ++i)
-        sts128(strip + (uint32_t)i * 512u, make_float4(0.f, 0.f, 0.f, 0.f));
+    a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+}
+__device__ __forceinline__ float4 mul4(float w, const float4 &v)
+{
+    return make_float4(w * v.x, w * v.y, w * v.z, w * v.w);
+}
+
+template <int NX, int R>
+__device__ __forceinline__ float4 taps(const float4 (&V)[kSW], const float4 w)
+{
+    float4 o = mul4(w.x, V[R]);
+    if (NX > 1 && R + 1 < kSW) fma4(o, w.y, V[R + 1]);
+    if (NX > 2 && R + 2 < kSW) fma4(o, w.z, V[R + 2]);
+    if (NX > 3 && R + 3 < kSW) fma4(o, w.w, V[R + 3]);
+    return o;
 }
 
 template <int NX>
 __device__ __forceinline__ void fwd_bin_pass(const AxisTab &xt, int pa, int pb, int lo_a, int C,
-                                             uint32_t strip, float *__restrict__ out, bool active)
+                                             const float4 (&V)[kSW], float *__restrict__ out, bool active)
 {
-#pragma unroll 2
-    for (int pw = pa; pw < pb; ++pw) {
-        const uint32_t a = strip + (uint32_t)(xt.lo[pw] - lo_a) * 512u;
+    float *o_ptr = out + (size_t)pa * C;
+    for (int pw = pa; pw < pb; ++pw, o_ptr += C) {
+        const int r = xt.lo[pw] - lo_a;
         const float4 w = xt.w[pw];
-        float4 v = lds128(a), o;
-        o.x = w.x * v.x; o.y = w.x * v.y; o.z = w.x * v.z; o.w = w.x * v.w;
-        if (NX > 1) { v = lds128(a + 512u);
-                      o.x = fmaf(w.y, v.x, o.x); o.y = fmaf(w.y, v.y, o.y); o.z = fmaf(w.y, v.z, o.z); o.w = fmaf(w.y, v.w, o.w); }
-        if (NX > 2) { v = lds128(a + 1024u);
-                      o.x = fmaf(w.z, v.x, o.x); o.y = fmaf(w.z, v.y, o.y); o.z = fmaf(w.z, v.z, o.z); o.w = fmaf(w.z, v.w, o.w); }
-        if (NX > 3) { v = lds128(a + 1536u);
-                      o.x = fmaf(w.w, v.x, o.x); o.y = fmaf(w.w, v.y, o.y); o.z = fmaf(w.w, v.z, o.z); o.w = fmaf(w.w, v.w, o.w); }
-        if (active) stg_stream128(out + (size_t)pw * C, o);
+        float4 o;
+        switch (r) {
+        case 0: o = taps<NX, 0>(V, w); break;
+        case 1: o = taps<NX, 1>(V, w); break;
+        case 2: o = taps<NX, 2>(V, w); break;
+        case 3: o = taps<NX, 3>(V, w); break;
+        case 4: o = taps<NX, 4>(V, w); break;
+        case 5: o = taps<NX, 5>(V, w); break;
+        case 6: o = taps<NX, 6>(V, w); break;
+        default: o = taps<NX, 7>(V, w); break;
+        }
+        if (active) stg_stream128(o_ptr, o);
     }
 }
 
-__global__ void __launch_bounds__(kMaxThreads, 3)
-rpool_forward_kernel(const __grid_constant__ KParams P)
+template <int kC>
+__device__ __forceinline__ void fwd_load_row(float4 (&t)[kSW], const float *__restrict__ p, int C,
+                                             int count, bool active)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    BlockCtl *ctl = reinterpret_cast<BlockCtl *>(smem_raw);
-    constexpr int kCtlBytes = (sizeof(BlockCtl) + 127) & ~127;
+#pragma unroll
+    for (int s = 0; s < kSW; ++s) {
+        t[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && s < count) t[s] = ldg_nc128(p + (kC ? s * kC : s * C));
+    }
+}
 
-    RoiCtx c;
-    roi_prologue(P, false, c);
-    if (!c.fast_ok || !c.valid) {
-        generic_forward(P, c);
-        return;
-    }
-    build_tables(P, c, ctl);
-    if (!ctl->eligible) {
-        generic_forward(P, c);
-        return;
-    }
-    const int C = P.C;
+template <int kC>
+__device__ __forceinline__ void fwd_tasks(const KParams &P, const RoiCtx &c, const BlockCtl *ctl)
+{
+    const int C = kC ? kC : P.C;
     const int wx1 = ctl->wmax[1];
     const int slabs = (C + 127) >> 7;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const uint32_t strip = smem_u32(smem_raw + kCtlBytes) + (uint32_t)warp * (uint32_t)P.strip_cols * 512u +
-                           (uint32_t)lane * 16u;
-    const int SC = P.strip_cols;
     const int row_stride = c.L.W * C;
     const float *img = c.L.data + (size_t)c.b * c.L.H * row_stride;
 
@@ -338,45 +321,97 @@ rpool_forward_kernel(const __grid_constant__ KParams P)
         }
         const float4 wy = yt.w[ph];
         const float *rowp = img + (size_t)yt.lo[ph] * row_stride + ch;
-        int pa = 0;
-        while (pa < PW) {
+        const int nchunk = ctl->nchunk[h];
+        for (int q = 0; q < nchunk; ++q) {
+            const int pa = ctl->cstart[h][q], pb = ctl->cstart[h][q + 1];
             const int lo_a = xt.lo[pa];
-            int pb = pa + 1;
-            while (pb < PW && xt.lo[pb] + NX - lo_a <= SC) ++pb;
-            const int last = xt.lo[pb - 1] + NX - 1;          // last strip column any tap addresses
-            const int total = last - lo_a + 1;
+            const int last = xt.lo[pb - 1] + NX - 1;
             const int count = (last < wx1 ? last : wx1) - lo_a + 1;  // columns that exist in the window
-            const float *src = rowp + (size_t)lo_a * C;
-            switch (ny) {
-            case 1: fwd_col_pass<1>(src, row_stride, C, count, total, wy, strip, active); break;
-            case 2: fwd_col_pass<2>(src, row_stride, C, count, total, wy, strip, active); break;
-            case 3: fwd_col_pass<3>(src, row_stride, C, count, total, wy, strip, active); break;
-            default: fwd_col_pass<4>(src, row_stride, C, count, total, wy, strip, active); break;
+            const float *p = rowp + (size_t)lo_a * C;
+            float4 V[kSW], tmp[kSW];
+            fwd_load_row<kC>(tmp, p, C, count, active);
+#pragma unroll
+            for (int s = 0; s < kSW; ++s) V[s] = mul4(wy.x, tmp[s]);
+            if (ny > 1) {
+                fwd_load_row<kC>(tmp, p + row_stride, C, count, active);
+#pragma unroll
+                for (int s = 0; s < kSW; ++s) fma4(V[s], wy.y, tmp[s]);
             }
-            __syncwarp();
-            switch (NX) {
-            case 1: fwd_bin_pass<1>(xt, pa, pb, lo_a, C, strip, out, active); break;
-            case 2: fwd_bin_pass<2>(xt, pa, pb, lo_a, C, strip, out, active); break;
-            case 3: fwd_bin_pass<3>(xt, pa, pb, lo_a, C, strip, out, active); break;
-            default: fwd_bin_pass<4>(xt, pa, pb, lo_a, C, strip, out, active); break;
+            if (ny > 2) {
+                fwd_load_row<kC>(tmp, p + 2 * (size_t)row_stride, C, count, active);
+#pragma unroll
+                for (int s = 0; s < kSW; ++s) fma4(V[s], wy.z, tmp[s]);
             }
-            __syncwarp();
-            pa = pb;
+            if (ny > 3) {
+                fwd_load_row<kC>(tmp, p + 3 * (size_t)row_stride, C, count, active);
+#pragma unroll
+                for (int s = 0; s < kSW; ++s) fma4(V[s], wy.w, tmp[s]);
+            }
+            if (NX <= 2) fwd_bin_pass<2>(xt, pa, pb, lo_a, C, V, out, active);
+            else if (NX == 3) fwd_bin_pass<3>(xt, pa, pb, lo_a, C, V, out, active);
+            else fwd_bin_pass<4>(xt, pa, pb, lo_a, C, V, out, active);
         }
     }
+}
+
+// Cuts every head's bins into chunks whose x footprints span at most kSW columns.
+__device__ __forceinline__ void build_chunks(const KParams &P, BlockCtl *ctl)
+{
+    if (threadIdx.x < P.n_heads) {
+        const int h = threadIdx.x;
+        const AxisTab &xt = ctl->tab[h][1];
+        const int PW = P.PW[h];
+        int NX = ctl->nmax[h][1];
+        NX = NX < 2 ? 2 : NX;
+        int n = 0, pa = 0;
+        while (pa < PW) {
+            ctl->cstart[h][n++] = (unsigned char)pa;
+            const int lo_a = xt.lo[pa];
+            int pb = pa + 1;
+            while (pb < PW && xt.lo[pb] + NX - lo_a <= kSW) ++pb;
+            pa = pb;
+        }
+        ctl->cstart[h][n] = (unsigned char)PW;
+        ctl->nchunk[h] = n;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kMaxThreads, 3)
+rpool_forward_kernel(const __grid_constant__ KParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    BlockCtl *ctl = reinterpret_cast<BlockCtl *>(smem_raw);
+
+    RoiCtx c;
+    roi_prologue(P, false, c);
+    if (!c.fast_ok || !c.valid) {
+        generic_forward(P, c);
+        return;
+    }
+    build_tables(P, c, ctl);
+    if (!ctl->eligible) {
+        generic_forward(P, c);
+        return;
+    }
+    build_chunks(P, ctl);
+    if (P.C == 256) fwd_tasks<256>(P, c, ctl);
+    else fwd_tasks<0>(P, c, ctl);
 }
 
 // ---------------------------------------------------------------------------
 // table path, backward
 // ---------------------------------------------------------------------------
 // The adjoint as a gather, so that no two warps ever add to the same place:
-// task = (window row y, 128-channel slab), one warp each.  Per task:
+// task = (window row y, 128-channel slab), one warp each.  Per task and head:
 //   row pass     Z[pw] = sum over bin rows ph covering y of wyT[y][ph] * gy[ph][pw]
-//                (128-bit loads, every load independent), written to the warp's strip;
+//                (128-bit loads, kZ independent loads per bin row), written to the
+//                warp's strip in shared memory;
 //   column pass  G[x] = sum over bins pw covering x of wxT[x][pw] * Z[pw];
 //                one 128-bit vector reduction per window cell into the dense gradient.
 // The transposed weight tables (dense, kExt x kPBwd per axis) are built in
-// shared memory from the forward footprint tables.
+// shared memory from the forward footprint tables.  gy of the RoI that a later
+// CTA will handle is pulled into L2 with one bulk prefetch per bin row.
 struct TTab {
     float w[kExt][kPBwd];
     int pa[kExt], pb[kExt];  // covering bins of row/column i: [pa, pb)
@@ -421,6 +456,77 @@ __device__ __forceinline__ void build_ttabs(const KParams &P, const BlockCtl *ct
 
 constexpr int kZ = 7;  // bins per register chunk of the row pass
 
+// kC as in the forward kernel; kExact: PW is a multiple of kZ and C of 128, so
+// no lane and no chunk position is ever masked.
+template <int kC, bool kExact>
+__device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, const BlockCtl *ctl,
+                                          const TTab *tt, uint32_t strip)
+{
+    const int C = kC ? kC : P.C;
+    const int slabs = (C + 127) >> 7;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int x0 = ctl->wmin[1], y0 = ctl->wmin[0];
+    const int Hc = ctl->wmax[0] - y0 + 1, Wc = ctl->wmax[1] - x0 + 1;
+    float *img = c.L.data + (size_t)c.b * c.L.H * c.L.W * C;
+
+    const int ntask = Hc * slabs;
+    for (int t = warp; t < ntask; t += nwarps) {
+        const int i = t / slabs;
+        const int ch = (t - i * slabs) * 128 + lane * 4;
+        const bool active = kExact || ch < C;
+        float *grow = img + ((size_t)(y0 + i) * c.L.W + x0) * C + ch;
+        for (int h = 0; h < P.n_heads; ++h) {
+            const TTab &Ty = tt[h * 2];
+            const int PH = P.PH[h], PW = P.PW[h];
+            const int pa = Ty.pa[i], pb = Ty.pb[i];
+            if (pa >= pb) continue;  // a window row between this head's footprints
+            // ---- row pass
+            const float *gbase = P.pooled[h] + ((size_t)c.r * PH + pa) * PW * C + ch;
+            const int gstep = PW * C;
+            for (int pw0 = 0; pw0 < PW; pw0 += kZ) {
+                float4 Z[kZ];
+#pragma unroll
+                for (int k = 0; k < kZ; ++k) Z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float *g = gbase + (size_t)pw0 * C;
+                const float *wrow = &Ty.w[i][0];
+                for (int ph = pa; ph < pb; ++ph, g += gstep) {
+                    const float w = wrow[ph];
+                    float4 v[kZ];
+#pragma unroll
+                    for (int k = 0; k < kZ; ++k) {
+                        if (kExact) {
+                            v[k] = ldg_nc128(g + (kC ? k * kC : k * C));
+                        } else {
+                            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (active && pw0 + k < PW) v[k] = ldg_nc128(g + (size_t)k * C);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kZ; ++k) fma4(Z[k], w, v[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < kZ; ++k)
+                    if (kExact || pw0 + k < PW) sts128(strip + (uint32_t)(pw0 + k) * 512u, Z[k]);
+            }
+            __syncwarp();
+            // ---- column pass
+            const TTab &Tx = tt[h * 2 + 1];
+            float *gp = grow;
+            for (int j = 0; j < Wc; ++j, gp += C) {
+                const int qa = Tx.pa[j], qb = Tx.pb[j];
+                if (qa >= qb) continue;
+                float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float *wcol = &Tx.w[j][0];
+                uint32_t a = strip + (uint32_t)qa * 512u;
+#pragma unroll 2
+                for (int pw = qa; pw < qb; ++pw, a += 512u) fma4(G, wcol[pw], lds128(a));
+                if (active) red_add_v4(gp, G);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kMaxThreads, 3)
 rpool_backward_kernel(const __grid_constant__ KParams P)
 {
@@ -429,6 +535,23 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     constexpr int kCtlBytes = (sizeof(BlockCtl) + 127) & ~127;
     constexpr int kTTabBytes = (sizeof(TTab) + 127) & ~127;
     TTab *tt = reinterpret_cast<TTab *>(smem_raw + kCtlBytes);
+
+    // pull the upstream gradient of a RoI scheduled `prefetch` CTAs later into L2
+    if (P.prefetch > 0 && P.pool_layout == RPOOL_NHWC && (P.C & 3) == 0) {
+        const int nb = blockIdx.x + P.prefetch;
+        if (nb < P.R) {
+            int row = threadIdx.x;
+            for (int h = 0; h < P.n_heads; ++h) {
+                if (row >= 0 && row < P.PH[h]) {
+                    const int r2 = P.order[nb];
+                    const size_t row_floats = (size_t)P.PW[h] * P.C;
+                    prefetch_l2_bulk(P.pooled[h] + ((size_t)r2 * P.PH[h] + row) * row_floats,
+                                     (unsigned)(row_floats * 4));
+                }
+                row -= P.PH[h];
+            }
+        }
+    }
 
     RoiCtx c;
     roi_prologue(P, true, c);
@@ -449,82 +572,13 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     if (x1 < x0 || y1 < y0) return;
     build_ttabs(P, ctl, tt);
 
-    const int C = P.C;
-    const int slabs = (C + 127) >> 7;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t strip = smem_u32(smem_raw + kCtlBytes + P.n_heads * 2 * kTTabBytes) +
                            (uint32_t)warp * (uint32_t)P.strip_cols * 512u + (uint32_t)lane * 16u;
-    const int Hc = y1 - y0 + 1, Wc = x1 - x0 + 1;
-    float *img = c.L.data + (size_t)c.b * c.L.H * c.L.W * C;
-
-    const int ntask = Hc * slabs;
-    for (int t = warp; t < ntask; t += nwarps) {
-        const int i = t / slabs;
-        const int ch = (t - i * slabs) * 128 + lane * 4;
-        const bool active = ch < C;
-        // ---- row pass
-        unsigned hmask = 0;
-        int soff = 0;
-        for (int h = 0; h < P.n_heads; ++h) {
-            const TTab &T = tt[h * 2];
-            const int PH = P.PH[h], PW = P.PW[h];
-            const int pa = T.pa[i], pb = T.pb[i];
-            if (pa < pb) {
-                hmask |= 1u << h;
-                const float *gbase = P.pooled[h] + ((size_t)c.r * PH * PW) * C + ch;
-                for (int pw0 = 0; pw0 < PW; pw0 += kZ) {
-                    float4 Z[kZ];
-#pragma unroll
-                    for (int k = 0; k < kZ; ++k) Z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int ph = pa; ph < pb; ++ph) {
-                        const float w = T.w[i][ph];
-                        const float *g = gbase + ((size_t)ph * PW + pw0) * C;
-                        float4 v[kZ];
-#pragma unroll
-                        for (int k = 0; k < kZ; ++k) {
-                            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (active && pw0 + k < PW) v[k] = ldg_nc128(g + (size_t)k * C);
-                        }
-#pragma unroll
-                        for (int k = 0; k < kZ; ++k) {
-                            Z[k].x = fmaf(w, v[k].x, Z[k].x); Z[k].y = fmaf(w, v[k].y, Z[k].y);
-                            Z[k].z = fmaf(w, v[k].z, Z[k].z); Z[k].w = fmaf(w, v[k].w, Z[k].w);
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < kZ; ++k)
-                        if (pw0 + k < PW) sts128(strip + (uint32_t)(soff + pw0 + k) * 512u, Z[k]);
-                }
-            }
-            soff += PW;
-        }
-        if (hmask == 0) continue;  // a window row between footprints: nothing lands on it
-        __syncwarp();
-        // ---- column pass
-        float *grow = img + ((size_t)(y0 + i) * c.L.W + x0) * C + ch;
-        for (int j = 0; j < Wc; ++j) {
-            float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
-            bool any = false;
-            soff = 0;
-            for (int h = 0; h < P.n_heads; ++h) {
-                if (hmask & (1u << h)) {
-                    const TTab &T = tt[h * 2 + 1];
-                    const int qa = T.pa[j], qb = T.pb[j];
-                    any = any || (qa < qb);
-#pragma unroll 2
-                    for (int pw = qa; pw < qb; ++pw) {
-                        const float w = T.w[j][pw];
-                        const float4 z = lds128(strip + (uint32_t)(soff + pw) * 512u);
-                        G.x = fmaf(w, z.x, G.x); G.y = fmaf(w, z.y, G.y);
-                        G.z = fmaf(w, z.z, G.z); G.w = fmaf(w, z.w, G.w);
-                    }
-                }
-                soff += P.PW[h];
-            }
-            if (any && active) red_add_v4(grow + (size_t)j * C, G);
-        }
-        __syncwarp();
-    }
+    bool exact = (P.C == 256);
+    for (int h = 0; h < P.n_heads; ++h) exact = exact && (P.PW[h] % kZ == 0);
+    if (exact) bwd_tasks<256, true>(P, c, ctl, tt, strip);
+    else bwd_tasks<0, false>(P, c, ctl, tt, strip);
 }
 
 // ---------------------------------------------------------------------------

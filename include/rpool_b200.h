@@ -134,7 +134,7 @@ RPOOL_API const char *rpool_last_error(void);
 /* Number of kernels this library has launched in the calling process. */
 RPOOL_API uint64_t rpool_launch_count(void);
 
-/* Tuning knobs for experiments ("strip_cols", "threads", "order", "force_path").
+/* Tuning knobs for experiments ("prefetch", "threads", "order", "force_path").
  * Unknown keys return RPOOL_ERR_INVALID. */
 RPOOL_API int rpool_set_tuning(const char *key, int value);
 RPOOL_API int rpool_get_tuning(const char *key, int *value);

@@ -55,10 +55,10 @@ def test_thresholds_libc_equal_numpy():
 
 
 def test_tuning_roundtrip_and_errors():
-    old = _lib.get_tuning("strip_cols")
-    _lib.set_tuning(strip_cols=9)
-    assert _lib.get_tuning("strip_cols") == 9
-    _lib.set_tuning(strip_cols=old)
+    old = _lib.get_tuning("prefetch")
+    _lib.set_tuning(prefetch=9)
+    assert _lib.get_tuning("prefetch") == 9
+    _lib.set_tuning(prefetch=old)
     with pytest.raises(_lib.RpoolError):
         _lib.set_tuning(threads=100)
     with pytest.raises(_lib.RpoolError):

@@ -27,7 +27,7 @@ PATHS = {"auto": _lib.PATH_AUTO, "generic": _lib.PATH_GENERIC, "table": _lib.PAT
 
 @pytest.fixture(autouse=True)
 def _reset_tuning():
-    defaults = {k: _lib.get_tuning(k) for k in ("strip_cols", "threads", "order", "force_path")}
+    defaults = {k: _lib.get_tuning(k) for k in ("prefetch", "threads", "order", "force_path")}
     yield
     _lib.set_tuning(**defaults)
 
@@ -159,12 +159,11 @@ def test_levels_random_million_bit_exact():
 # ---------------------------------------------------------------------------
 # seeded random cases against the oracle, every kernel path
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("path,strip_cols", [("auto", 12), ("generic", 12), ("table", 12),
-                                             ("table", 4), ("table", 7), ("auto", 40)])
+@pytest.mark.parametrize("path,prefetch", [("auto", 148), ("generic", 0), ("table", 0), ("table", 7)])
 @pytest.mark.parametrize("mode_name,S", [("chainer", 1), ("caffe2", 1), ("caffe2", 2), ("caffe2", 3)])
-def test_fused_vs_oracle(path, strip_cols, mode_name, S):
+def test_fused_vs_oracle(path, prefetch, mode_name, S):
     rng, feats, rois, levels, scales = make_case(seed=S * 7 + len(path))
-    _lib.set_tuning(force_path=PATHS[path], strip_cols=strip_cols)
+    _lib.set_tuning(force_path=PATHS[path], prefetch=prefetch)
     mode = _lib.COORD_CHAINER if mode_name == "chainer" else _lib.COORD_CAFFE2
     sizes = [7, 14]
     gys = [synth.make_gy(rng, rois.shape[0], feats[0].shape[1], P) for P in sizes]
