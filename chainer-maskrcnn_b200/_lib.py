@@ -73,8 +73,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if _build.is_stale():
+    path = os.environ.get("RPOOL_B200_LIB") or _build.LIB_PATH   # override: experiments only
+    if path == _build.LIB_PATH and _build.is_stale():
         try:
             _build.build()
         except Exception as e:  # noqa: BLE001

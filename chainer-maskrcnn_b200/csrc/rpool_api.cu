@@ -17,9 +17,11 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 
+constexpr int kMaxSmem = 227 * 1024;
+
 // tuning knobs (process-wide; experiments only)
-std::atomic<int> g_prefetch{0};
-std::atomic<int> g_threads{256};
+std::atomic<int> g_prefetch{-1};
+std::atomic<int> g_threads{128};
 std::atomic<int> g_order{1};
 std::atomic<int> g_force_path{kPathAuto};
 
@@ -115,8 +117,6 @@ int validate(const rpool_problem *p, void *ws, size_t ws_size, bool need_pooled)
     return RPOOL_OK;
 }
 
-constexpr int kMaxSmem = 227 * 1024;
-
 // Fills the kernel parameter block; returns the dynamic shared memory the
 // launch needs (control block + per-warp strips [+ transposed tables]).
 int fill_params(const rpool_problem *p, const Workspace &w, bool bwd, int threads, KParams &k)
@@ -182,8 +182,8 @@ int rpool_set_tuning(const char *key, int value)
 {
     if (!key) return fail(RPOOL_ERR_INVALID, "key is NULL");
     if (!strcmp(key, "prefetch")) {
-        if (value < 0 || value > 65536)
-            return fail(RPOOL_ERR_INVALID, "prefetch=%d outside [0,65536]", value);
+        if (value < -1 || value > 65536)
+            return fail(RPOOL_ERR_INVALID, "prefetch=%d outside [-1,65536]", value);
         g_prefetch = value;
     } else if (!strcmp(key, "threads")) {
         if (value < 32 || value > kMaxThreads || value % 32)

@@ -16,7 +16,11 @@ namespace rpool {
 constexpr int kNT = 4;        // footprint width kept per bin and axis on the table path
 constexpr int kPMax = 32;     // largest pooled extent served by the table path (forward)
 constexpr int kPBwd = 16;     // ... by the table path of the backward kernel
+constexpr int kSW = 8;        // window columns a chunk of bins may span (forward registers)
 constexpr int kExt = 64;      // largest window extent (cells per axis) of the backward table path
+#ifndef RPOOL_MIN_BLOCKS
+#define RPOOL_MIN_BLOCKS 2   // resident CTAs per SM the pooling kernels are register-capped for
+#endif
 constexpr int kMaxThreads = 256;  // CTA size the pooling kernels are compiled for
 constexpr int kMaxHeads = RPOOL_MAX_HEADS;
 constexpr int kMaxLevels = RPOOL_MAX_LEVELS;
@@ -45,7 +49,7 @@ struct KParams {
     int S;
     int mode;
     int strip_cols;  // backward: entries of a warp's strip (512 bytes each)
-    int prefetch;    // backward: L2 prefetch distance in CTAs (0 = off)
+    int prefetch;    // backward: L2 prefetch distance in CTAs (0 = own RoI, < 0 = off)
     int force_path;
 };
 
@@ -180,8 +184,11 @@ struct BlockCtl {
     int nmax[kMaxHeads][2];     // widest footprint of any bin, per head and axis
     int nchunk[kMaxHeads];      // forward: bins cut into chunks of bounded x extent
     unsigned char cstart[kMaxHeads][kPMax + 4];
+    int cx0[kMaxHeads][kPMax];                  // first column of each chunk's span
+    unsigned long long ccnt[kMaxHeads][kPMax];  // bins per span offset, one byte each
     int eligible;
     int pad_;
+    unsigned long long mbar;
 };
 
 // Fills entry p of `t`; returns false when the footprint does not fit kNT cells.

@@ -29,10 +29,18 @@ struct RoiCtx {
     bool valid;       // batch index inside the level's tensor
     bool fast_ok;     // layouts/alignment allow the table-driven paths at all
     LevelDev L;
-    AxisGeom gy[kMaxHeads], gx[kMaxHeads];
+    RoiBox box;
 };
 
-__device__ __forceinline__ void roi_prologue(const KParams &P, bool bwd, RoiCtx &c)
+// Geometry of one axis of head h (computed where it is needed only: keeping it
+// per thread for every head would live in local memory).
+__device__ __forceinline__ AxisGeom axis_of(const KParams &P, const RoiCtx &c, bool bwd, int h, int axis)
+{
+    return axis ? make_axis(P.mode, bwd, c.box.x1, c.box.x2, c.L.scale, P.PW[h], P.S, c.L.W)
+                : make_axis(P.mode, bwd, c.box.y1, c.box.y2, c.L.scale, P.PH[h], P.S, c.L.H);
+}
+
+__device__ __forceinline__ void roi_prologue(const KParams &P, RoiCtx &c)
 {
     c.r = P.order[blockIdx.x];
     int lvl = P.roi_level[c.r];
@@ -41,11 +49,8 @@ __device__ __forceinline__ void roi_prologue(const KParams &P, bool bwd, RoiCtx 
     c.L = P.lvl[lvl];
     const RoiBox q = load_roi(P.rois, c.r, P.roi_format);
     c.b = q.b;
+    c.box = q;
     c.valid = (q.b >= 0 && q.b < c.L.n_images);
-    for (int h = 0; h < P.n_heads; ++h) {
-        c.gy[h] = make_axis(P.mode, bwd, q.y1, q.y2, c.L.scale, P.PH[h], P.S, c.L.H);
-        c.gx[h] = make_axis(P.mode, bwd, q.x1, q.x2, c.L.scale, P.PW[h], P.S, c.L.W);
-    }
     bool ok = (P.feat_layout == RPOOL_NHWC) && (P.pool_layout == RPOOL_NHWC) && (P.C % 4 == 0);
     ok = ok && ((reinterpret_cast<uintptr_t>(c.L.data) & 15) == 0);
     for (int h = 0; h < P.n_heads; ++h) {
@@ -56,7 +61,7 @@ __device__ __forceinline__ void roi_prologue(const KParams &P, bool bwd, RoiCtx 
 }
 
 // Builds the tables; returns with ctl fully populated and the CTA synchronised.
-__device__ __forceinline__ void build_tables(const KParams &P, const RoiCtx &c, BlockCtl *ctl)
+__device__ __forceinline__ void build_tables(const KParams &P, const RoiCtx &c, bool bwd, BlockCtl *ctl)
 {
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -75,7 +80,7 @@ __device__ __forceinline__ void build_tables(const KParams &P, const RoiCtx &c, 
             const int axis = e < ny ? 0 : 1;
             const int p = axis ? e - ny : e;
             int lo, hi;
-            const bool ok = fill_axis_entry(ctl->tab[h][axis], axis ? c.gx[h] : c.gy[h], P.mode,
+            const bool ok = fill_axis_entry(ctl->tab[h][axis], axis_of(P, c, bwd, h, axis), P.mode,
                                             p, lo, hi);
             if (!ok) ctl->eligible = 0;
             if (hi >= lo) {
@@ -106,8 +111,12 @@ __device__ __forceinline__ Strides4 strides_of(int layout, int C, int H, int W)
     return s;
 }
 
-__device__ void generic_forward(const KParams &P, const RoiCtx &c)
+// (noinline, and decoding the RoI again itself, so that neither its registers nor
+// a spilled context reach the table path)
+__device__ __noinline__ void generic_forward(const KParams &P)
 {
+    RoiCtx c;
+    roi_prologue(P, c);
     const int C = P.C;
     const Strides4 fs = strides_of(P.feat_layout, C, c.L.H, c.L.W);
     const float *feat = c.L.data + (long long)(c.valid ? c.b : 0) * fs.s0;
@@ -115,7 +124,7 @@ __device__ void generic_forward(const KParams &P, const RoiCtx &c)
         const int PH = P.PH[h], PW = P.PW[h];
         const Strides4 os = strides_of(P.pool_layout, C, PH, PW);
         float *out = P.pooled[h] + (long long)c.r * os.s0;
-        const AxisGeom gy = c.gy[h], gx = c.gx[h];
+        const AxisGeom gy = axis_of(P, c, false, h, 0), gx = axis_of(P, c, false, h, 1);
         const int total = PH * PW * C;
         for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
             int ch, bin;
@@ -169,8 +178,10 @@ __device__ void generic_forward(const KParams &P, const RoiCtx &c)
     }
 }
 
-__device__ void generic_backward(const KParams &P, const RoiCtx &c)
+__device__ __noinline__ void generic_backward(const KParams &P)
 {
+    RoiCtx c;
+    roi_prologue(P, c);
     if (!c.valid) return;
     const int C = P.C;
     const Strides4 fs = strides_of(P.feat_layout, C, c.L.H, c.L.W);
@@ -179,7 +190,7 @@ __device__ void generic_backward(const KParams &P, const RoiCtx &c)
         const int PH = P.PH[h], PW = P.PW[h];
         const Strides4 os = strides_of(P.pool_layout, C, PH, PW);
         const float *gyp = P.pooled[h] + (long long)c.r * os.s0;
-        const AxisGeom gy = c.gy[h], gx = c.gx[h];
+        const AxisGeom gy = axis_of(P, c, true, h, 0), gx = axis_of(P, c, true, h, 1);
         const int total = PH * PW * C;
         for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
             int ch, bin;
@@ -224,19 +235,20 @@ __device__ void generic_backward(const KParams &P, const RoiCtx &c)
 // table path, forward
 // ---------------------------------------------------------------------------
 // Task = (head, bin row ph, 128-channel slab), one warp each; a lane owns 4
-// channels.  The row's bins are cut into chunks whose footprints span at most
-// kSW window columns.  Per chunk:
-//   column pass  V[s] = sum_j wy[j] * X[ylo + j][lo_a + s], s < kSW, kept in
+// channels.  The row's bins are cut into chunks whose footprints fit a span of
+// kSW window columns starting at column cx0 (chosen inside the image so that
+// all kSW columns exist: no load is ever masked).  Per chunk:
+//   column pass  V[s] = sum_j wy[j] * X[ylo + j][cx0 + s], s < kSW, kept in
 //                registers; 128-bit loads through L1 (a window row is re-read by
-//                the ~5 bin rows whose footprint contains it), all loads of one
-//                window row in flight together;
-//   bin pass     out[pw] = sum_k wx[pw][k] * V[lo[pw] - lo_a + k]: the offset is
-//                warp-uniform, so a switch on it selects code whose register
-//                operands are static; evict-first 128-bit stores.
+//                the ~5 bin rows whose footprint contains it), the kSW loads of
+//                one window row in flight together;
+//   bin pass     out[pw] = sum_k wx[pw][k] * V[lo[pw] - cx0 + k].  Bins are
+//                visited in order and their offsets lo[pw] - cx0 never decrease,
+//                so the pass is a static sequence over the kSW offsets, each
+//                running its (table-supplied) count of bins with compile-time
+//                register operands; evict-first 128-bit stores.
 // kC > 0 fixes the channel count at compile time (address arithmetic folds
 // into immediates); kC == 0 reads it from the parameters.
-constexpr int kSW = 8;
-
 __device__ __forceinline__ void fma4(float4 &a, float w, const float4 &v)
 {
     a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
@@ -249,6 +261,7 @@ __device__ __forceinline__ float4 mul4(float w, const float4 &v)
 template <int NX, int R>
 __device__ __forceinline__ float4 taps(const float4 (&V)[kSW], const float4 w)
 {
+    // taps past the span carry zero weight (they lie beyond the window)
     float4 o = mul4(w.x, V[R]);
     if (NX > 1 && R + 1 < kSW) fma4(o, w.y, V[R + 1]);
     if (NX > 2 && R + 2 < kSW) fma4(o, w.z, V[R + 2]);
@@ -256,45 +269,44 @@ __device__ __forceinline__ float4 taps(const float4 (&V)[kSW], const float4 w)
     return o;
 }
 
-template <int NX>
-__device__ __forceinline__ void fwd_bin_pass(const AxisTab &xt, int pa, int pb, int lo_a, int C,
-                                             const float4 (&V)[kSW], float *__restrict__ out, bool active)
+template <int NX, int R>
+__device__ __forceinline__ void fwd_bins_at(const float4 (&V)[kSW], unsigned long long cnt,
+                                            const float4 *&wp, float *&o_ptr, int C, bool active)
 {
-    float *o_ptr = out + (size_t)pa * C;
-    for (int pw = pa; pw < pb; ++pw, o_ptr += C) {
-        const int r = xt.lo[pw] - lo_a;
-        const float4 w = xt.w[pw];
-        float4 o;
-        switch (r) {
-        case 0: o = taps<NX, 0>(V, w); break;
-        case 1: o = taps<NX, 1>(V, w); break;
-        case 2: o = taps<NX, 2>(V, w); break;
-        case 3: o = taps<NX, 3>(V, w); break;
-        case 4: o = taps<NX, 4>(V, w); break;
-        case 5: o = taps<NX, 5>(V, w); break;
-        case 6: o = taps<NX, 6>(V, w); break;
-        default: o = taps<NX, 7>(V, w); break;
-        }
+    const int n = (int)((cnt >> (8 * R)) & 0xffull);
+    for (int i = 0; i < n; ++i) {
+        const float4 o = taps<NX, R>(V, *wp);
         if (active) stg_stream128(o_ptr, o);
+        ++wp;
+        o_ptr += C;
     }
 }
 
+template <int NX>
+__device__ __forceinline__ void fwd_bin_pass(const float4 (&V)[kSW], unsigned long long cnt,
+                                             const float4 *wp, float *o_ptr, int C, bool active)
+{
+    fwd_bins_at<NX, 0>(V, cnt, wp, o_ptr, C, active);
+    fwd_bins_at<NX, 1>(V, cnt, wp, o_ptr, C, active);
+    fwd_bins_at<NX, 2>(V, cnt, wp, o_ptr, C, active);
+    fwd_bins_at<NX, 3>(V, cnt, wp, o_ptr, C, active);
+    fwd_bins_at<NX, 4>(V, cnt, wp, o_ptr, C, active);
+    fwd_bins_at<NX, 5>(V, cnt, wp, o_ptr, C, active);
+    fwd_bins_at<NX, 6>(V, cnt, wp, o_ptr, C, active);
+    fwd_bins_at<NX, 7>(V, cnt, wp, o_ptr, C, active);
+}
+
 template <int kC>
-__device__ __forceinline__ void fwd_load_row(float4 (&t)[kSW], const float *__restrict__ p, int C,
-                                             int count, bool active)
+__device__ __forceinline__ void fwd_load_row(float4 (&t)[kSW], const float *__restrict__ p, int C)
 {
 #pragma unroll
-    for (int s = 0; s < kSW; ++s) {
-        t[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active && s < count) t[s] = ldg_nc128(p + (kC ? s * kC : s * C));
-    }
+    for (int s = 0; s < kSW; ++s) t[s] = ldg_nc128(p + (kC ? s * kC : s * C));
 }
 
 template <int kC>
 __device__ __forceinline__ void fwd_tasks(const KParams &P, const RoiCtx &c, const BlockCtl *ctl)
 {
     const int C = kC ? kC : P.C;
-    const int wx1 = ctl->wmax[1];
     const int slabs = (C + 127) >> 7;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int row_stride = c.L.W * C;
@@ -320,55 +332,72 @@ __device__ __forceinline__ void fwd_tasks(const KParams &P, const RoiCtx &c, con
             continue;
         }
         const float4 wy = yt.w[ph];
-        const float *rowp = img + (size_t)yt.lo[ph] * row_stride + ch;
+        // lanes past the last channel of a partial slab read channel 0 and store nothing
+        const float *rowp = img + (size_t)yt.lo[ph] * row_stride + (active ? ch : 0);
         const int nchunk = ctl->nchunk[h];
         for (int q = 0; q < nchunk; ++q) {
-            const int pa = ctl->cstart[h][q], pb = ctl->cstart[h][q + 1];
-            const int lo_a = xt.lo[pa];
-            const int last = xt.lo[pb - 1] + NX - 1;
-            const int count = (last < wx1 ? last : wx1) - lo_a + 1;  // columns that exist in the window
-            const float *p = rowp + (size_t)lo_a * C;
+            const int pa = ctl->cstart[h][q];
+            const unsigned long long cnt = ctl->ccnt[h][q];
+            const float *p = rowp + (size_t)ctl->cx0[h][q] * C;
             float4 V[kSW], tmp[kSW];
-            fwd_load_row<kC>(tmp, p, C, count, active);
+            fwd_load_row<kC>(tmp, p, C);
 #pragma unroll
             for (int s = 0; s < kSW; ++s) V[s] = mul4(wy.x, tmp[s]);
             if (ny > 1) {
-                fwd_load_row<kC>(tmp, p + row_stride, C, count, active);
+                fwd_load_row<kC>(tmp, p + row_stride, C);
 #pragma unroll
                 for (int s = 0; s < kSW; ++s) fma4(V[s], wy.y, tmp[s]);
             }
             if (ny > 2) {
-                fwd_load_row<kC>(tmp, p + 2 * (size_t)row_stride, C, count, active);
+                fwd_load_row<kC>(tmp, p + 2 * (size_t)row_stride, C);
 #pragma unroll
                 for (int s = 0; s < kSW; ++s) fma4(V[s], wy.z, tmp[s]);
             }
             if (ny > 3) {
-                fwd_load_row<kC>(tmp, p + 3 * (size_t)row_stride, C, count, active);
+                fwd_load_row<kC>(tmp, p + 3 * (size_t)row_stride, C);
 #pragma unroll
                 for (int s = 0; s < kSW; ++s) fma4(V[s], wy.w, tmp[s]);
             }
-            if (NX <= 2) fwd_bin_pass<2>(xt, pa, pb, lo_a, C, V, out, active);
-            else if (NX == 3) fwd_bin_pass<3>(xt, pa, pb, lo_a, C, V, out, active);
-            else fwd_bin_pass<4>(xt, pa, pb, lo_a, C, V, out, active);
+            const float4 *wp = &xt.w[pa];
+            float *o_ptr = out + (size_t)pa * C;
+            if (NX <= 2) fwd_bin_pass<2>(V, cnt, wp, o_ptr, C, active);
+            else if (NX == 3) fwd_bin_pass<3>(V, cnt, wp, o_ptr, C, active);
+            else fwd_bin_pass<4>(V, cnt, wp, o_ptr, C, active);
         }
     }
 }
 
-// Cuts every head's bins into chunks whose x footprints span at most kSW columns.
-__device__ __forceinline__ void build_chunks(const KParams &P, BlockCtl *ctl)
+// Cuts every head's bins into chunks whose x footprints fit a span of kSW
+// columns; records per chunk its first bin, the first column of the span and how
+// many of its bins start at each of the kSW offsets (one byte per offset).
+// max_bins bounds the bins per chunk (the backward pass keeps them in registers).
+__device__ __forceinline__ void build_chunks(const KParams &P, const RoiCtx &c, BlockCtl *ctl, int max_bins)
 {
     if (threadIdx.x < P.n_heads) {
         const int h = threadIdx.x;
         const AxisTab &xt = ctl->tab[h][1];
         const int PW = P.PW[h];
+        const int W = c.L.W;
         int NX = ctl->nmax[h][1];
-        NX = NX < 2 ? 2 : NX;
+        NX = NX < 1 ? 1 : NX;
         int n = 0, pa = 0;
         while (pa < PW) {
-            ctl->cstart[h][n++] = (unsigned char)pa;
+            ctl->cstart[h][n] = (unsigned char)pa;
             const int lo_a = xt.lo[pa];
-            int pb = pa + 1;
-            while (pb < PW && xt.lo[pb] + NX - lo_a <= kSW) ++pb;
+            int x0 = lo_a < W - kSW ? lo_a : W - kSW;   // span [x0, x0 + kSW) inside the image
+            x0 = x0 < 0 ? 0 : x0;
+            unsigned long long cnt = 0;
+            int pb = pa;
+            while (pb < PW && pb - pa < max_bins) {
+                const int last = xt.lo[pb] + NX - 1;
+                const int lim = last < W - 1 ? last : W - 1;   // taps beyond the image carry no weight
+                if (pb > pa && lim - x0 >= kSW) break;
+                cnt += 1ull << (8 * (xt.lo[pb] - x0));
+                ++pb;
+            }
+            ctl->cx0[h][n] = x0;
+            ctl->ccnt[h][n] = cnt;
+            ++n;
             pa = pb;
         }
         ctl->cstart[h][n] = (unsigned char)PW;
@@ -377,24 +406,25 @@ __device__ __forceinline__ void build_chunks(const KParams &P, BlockCtl *ctl)
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kMaxThreads, 3)
+__global__ void __launch_bounds__(kMaxThreads, RPOOL_MIN_BLOCKS)
 rpool_forward_kernel(const __grid_constant__ KParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockCtl *ctl = reinterpret_cast<BlockCtl *>(smem_raw);
 
     RoiCtx c;
-    roi_prologue(P, false, c);
-    if (!c.fast_ok || !c.valid) {
-        generic_forward(P, c);
+    roi_prologue(P, c);
+    // the table path reads spans of kSW columns: the map must be that wide
+    if (!c.fast_ok || !c.valid || c.L.W < kSW) {
+        generic_forward(P);
         return;
     }
-    build_tables(P, c, ctl);
+    build_tables(P, c, false, ctl);
     if (!ctl->eligible) {
-        generic_forward(P, c);
+        generic_forward(P);
         return;
     }
-    build_chunks(P, ctl);
+    build_chunks(P, c, ctl, kPMax);
     if (P.C == 256) fwd_tasks<256>(P, c, ctl);
     else fwd_tasks<0>(P, c, ctl);
 }
@@ -527,7 +557,7 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
     }
 }
 
-__global__ void __launch_bounds__(kMaxThreads, 3)
+__global__ void __launch_bounds__(kMaxThreads, RPOOL_MIN_BLOCKS)
 rpool_backward_kernel(const __grid_constant__ KParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -536,8 +566,9 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     constexpr int kTTabBytes = (sizeof(TTab) + 127) & ~127;
     TTab *tt = reinterpret_cast<TTab *>(smem_raw + kCtlBytes);
 
-    // pull the upstream gradient of a RoI scheduled `prefetch` CTAs later into L2
-    if (P.prefetch > 0 && P.pool_layout == RPOOL_NHWC && (P.C & 3) == 0) {
+    // pull the upstream gradient of the RoI scheduled `prefetch` CTAs later (0: this
+    // CTA's own, overlapping the table construction below) into L2
+    if (P.prefetch >= 0 && P.pool_layout == RPOOL_NHWC && (P.C & 3) == 0) {
         const int nb = blockIdx.x + P.prefetch;
         if (nb < P.R) {
             int row = threadIdx.x;
@@ -554,19 +585,19 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     }
 
     RoiCtx c;
-    roi_prologue(P, true, c);
+    roi_prologue(P, c);
     if (!c.valid) return;
     bool table_ok = c.fast_ok;
     for (int h = 0; h < P.n_heads; ++h) table_ok = table_ok && P.PH[h] <= kPBwd && P.PW[h] <= kPBwd;
     if (!table_ok) {
-        generic_backward(P, c);
+        generic_backward(P);
         return;
     }
-    build_tables(P, c, ctl);
+    build_tables(P, c, true, ctl);
     const int x0 = ctl->wmin[1], x1 = ctl->wmax[1];
     const int y0 = ctl->wmin[0], y1 = ctl->wmax[0];
     if (!ctl->eligible || x1 - x0 >= kExt || y1 - y0 >= kExt) {
-        generic_backward(P, c);
+        generic_backward(P);
         return;
     }
     if (x1 < x0 || y1 < y0) return;
