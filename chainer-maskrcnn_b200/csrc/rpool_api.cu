@@ -155,7 +155,7 @@ int fill_params(const rpool_problem *p, const Workspace &w, bool bwd, int thread
     if (!bwd) return ctl;
     const int ttab = (int)((sizeof(TTab) + 127) & ~(size_t)127);
     k.strip_cols = sum_pw > 0 ? sum_pw : 1;
-    return ctl + p->n_heads * 2 * ttab + warps * k.strip_cols * 512;
+    return ctl + p->n_heads * ttab + warps * k.strip_cols * 512;
 }
 
 template <typename Kern>

@@ -186,6 +186,7 @@ struct BlockCtl {
     unsigned char cstart[kMaxHeads][kPMax + 4];
     int cx0[kMaxHeads][kPMax];                  // first column of each chunk's span
     unsigned long long ccnt[kMaxHeads][kPMax];  // bins per span offset, one byte each
+    unsigned char cmask[kMaxHeads][kPMax];      // span offsets that carry any weight
     int eligible;
     int pad_;
     unsigned long long mbar;

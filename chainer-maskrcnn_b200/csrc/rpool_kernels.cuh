@@ -274,6 +274,7 @@ __device__ __forceinline__ void fwd_bins_at(const float4 (&V)[kSW], unsigned lon
                                             const float4 *&wp, float *&o_ptr, int C, bool active)
 {
     const int n = (int)((cnt >> (8 * R)) & 0xffull);
+#pragma unroll 1
     for (int i = 0; i < n; ++i) {
         const float4 o = taps<NX, R>(V, *wp);
         if (active) stg_stream128(o_ptr, o);
@@ -387,16 +388,19 @@ __device__ __forceinline__ void build_chunks(const KParams &P, const RoiCtx &c, 
             int x0 = lo_a < W - kSW ? lo_a : W - kSW;   // span [x0, x0 + kSW) inside the image
             x0 = x0 < 0 ? 0 : x0;
             unsigned long long cnt = 0;
+            unsigned mask = 0;
             int pb = pa;
             while (pb < PW && pb - pa < max_bins) {
                 const int last = xt.lo[pb] + NX - 1;
                 const int lim = last < W - 1 ? last : W - 1;   // taps beyond the image carry no weight
                 if (pb > pa && lim - x0 >= kSW) break;
                 cnt += 1ull << (8 * (xt.lo[pb] - x0));
+                mask |= ((1u << xt.n[pb]) - 1u) << (xt.lo[pb] - x0);
                 ++pb;
             }
             ctl->cx0[h][n] = x0;
             ctl->ccnt[h][n] = cnt;
+            ctl->cmask[h][n] = (unsigned char)(mask & 0xffu);
             ++n;
             pa = pb;
         }
@@ -439,8 +443,10 @@ rpool_forward_kernel(const __grid_constant__ KParams P)
 //                warp's strip in shared memory;
 //   column pass  G[x] = sum over bins pw covering x of wxT[x][pw] * Z[pw];
 //                one 128-bit vector reduction per window cell into the dense gradient.
-// The transposed weight tables (dense, kExt x kPBwd per axis) are built in
-// shared memory from the forward footprint tables.  gy of the RoI that a later
+//                Like the forward bin pass it walks the bins in order with the span
+//                offsets static, accumulating G[kSW] in registers.
+// The transposed y table (dense, kExt x kPBwd) is built in shared memory from the
+// forward footprint table.  gy of the RoI that a later
 // CTA will handle is pulled into L2 with one bulk prefetch per bin row.
 struct TTab {
     float w[kExt][kPBwd];
@@ -449,25 +455,22 @@ struct TTab {
 
 __device__ __forceinline__ void build_ttabs(const KParams &P, const BlockCtl *ctl, TTab *tt)
 {
+    // one transposed table per head, for the y axis: window row -> covering bin rows
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int ntab = P.n_heads * 2;
-    for (int a = 0; a < ntab; ++a) {
-        const int ext = ctl->wmax[a & 1] - ctl->wmin[a & 1] + 1;
-        float *w = &tt[a].w[0][0];
+    const int ext = ctl->wmax[0] - ctl->wmin[0] + 1;
+    for (int h = 0; h < P.n_heads; ++h) {
+        float *w = &tt[h].w[0][0];
         for (int i = tid; i < ext * kPBwd; i += nt) w[i] = 0.f;
-        for (int i = tid; i < ext; i += nt) { tt[a].pa[i] = 0x7fffffff; tt[a].pb[i] = 0; }
+        for (int i = tid; i < ext; i += nt) { tt[h].pa[i] = 0x7fffffff; tt[h].pb[i] = 0; }
     }
     __syncthreads();
     int base = 0;
     for (int h = 0; h < P.n_heads; ++h) {
-        const int ny = P.PH[h], nx = P.PW[h];
-        const int e = tid - base;
-        if (e >= 0 && e < ny + nx) {
-            const int axis = e < ny ? 0 : 1;
-            const int p = axis ? e - ny : e;
-            const AxisTab &t = ctl->tab[h][axis];
-            TTab &T = tt[h * 2 + axis];
-            const int n = t.n[p], row0 = t.lo[p] - ctl->wmin[axis];
+        const int p = tid - base;
+        if (p >= 0 && p < P.PH[h]) {
+            const AxisTab &t = ctl->tab[h][0];
+            TTab &T = tt[h];
+            const int n = t.n[p], row0 = t.lo[p] - ctl->wmin[0];
             const float4 w4 = t.w[p];
             const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
@@ -479,12 +482,44 @@ __device__ __forceinline__ void build_ttabs(const KParams &P, const BlockCtl *ct
                 }
             }
         }
-        base += ny + nx;
+        base += P.PH[h];
     }
     __syncthreads();
 }
 
 constexpr int kZ = 7;  // bins per register chunk of the row pass
+
+template <int NX, int R>
+__device__ __forceinline__ void bwd_bins_at(float4 (&G)[kSW], unsigned long long cnt, const float4 *&wp,
+                                            uint32_t &zp)
+{
+    const int n = (int)((cnt >> (8 * R)) & 0xffull);
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        const float4 w = *wp;
+        const float4 z = lds128(zp);
+        fma4(G[R], w.x, z);
+        if (NX > 1 && R + 1 < kSW) fma4(G[R + 1], w.y, z);
+        if (NX > 2 && R + 2 < kSW) fma4(G[R + 2], w.z, z);
+        if (NX > 3 && R + 3 < kSW) fma4(G[R + 3], w.w, z);
+        ++wp;
+        zp += 512u;
+    }
+}
+
+template <int NX>
+__device__ __forceinline__ void bwd_col_pass(float4 (&G)[kSW], unsigned long long cnt, const float4 *wp,
+                                             uint32_t zp)
+{
+    bwd_bins_at<NX, 0>(G, cnt, wp, zp);
+    bwd_bins_at<NX, 1>(G, cnt, wp, zp);
+    bwd_bins_at<NX, 2>(G, cnt, wp, zp);
+    bwd_bins_at<NX, 3>(G, cnt, wp, zp);
+    bwd_bins_at<NX, 4>(G, cnt, wp, zp);
+    bwd_bins_at<NX, 5>(G, cnt, wp, zp);
+    bwd_bins_at<NX, 6>(G, cnt, wp, zp);
+    bwd_bins_at<NX, 7>(G, cnt, wp, zp);
+}
 
 // kC as in the forward kernel; kExact: PW is a multiple of kZ and C of 128, so
 // no lane and no chunk position is ever masked.
@@ -495,8 +530,8 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
     const int C = kC ? kC : P.C;
     const int slabs = (C + 127) >> 7;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int x0 = ctl->wmin[1], y0 = ctl->wmin[0];
-    const int Hc = ctl->wmax[0] - y0 + 1, Wc = ctl->wmax[1] - x0 + 1;
+    const int y0 = ctl->wmin[0];
+    const int Hc = ctl->wmax[0] - y0 + 1;
     float *img = c.L.data + (size_t)c.b * c.L.H * c.L.W * C;
 
     const int ntask = Hc * slabs;
@@ -504,9 +539,9 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
         const int i = t / slabs;
         const int ch = (t - i * slabs) * 128 + lane * 4;
         const bool active = kExact || ch < C;
-        float *grow = img + ((size_t)(y0 + i) * c.L.W + x0) * C + ch;
+        float *grow_img = img + (size_t)(y0 + i) * c.L.W * C + ch;   // column 0 of the window row
         for (int h = 0; h < P.n_heads; ++h) {
-            const TTab &Ty = tt[h * 2];
+            const TTab &Ty = tt[h];
             const int PH = P.PH[h], PW = P.PW[h];
             const int pa = Ty.pa[i], pb = Ty.pb[i];
             if (pa >= pb) continue;  // a window row between this head's footprints
@@ -539,18 +574,26 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
                     if (kExact || pw0 + k < PW) sts128(strip + (uint32_t)(pw0 + k) * 512u, Z[k]);
             }
             __syncwarp();
-            // ---- column pass
-            const TTab &Tx = tt[h * 2 + 1];
-            float *gp = grow;
-            for (int j = 0; j < Wc; ++j, gp += C) {
-                const int qa = Tx.pa[j], qb = Tx.pb[j];
-                if (qa >= qb) continue;
-                float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
-                const float *wcol = &Tx.w[j][0];
-                uint32_t a = strip + (uint32_t)qa * 512u;
-#pragma unroll 2
-                for (int pw = qa; pw < qb; ++pw, a += 512u) fma4(G, wcol[pw], lds128(a));
-                if (active) red_add_v4(gp, G);
+            // ---- column pass: bins in order, span offsets static (as in the forward bin pass)
+            const AxisTab &xt = ctl->tab[h][1];
+            const int NX = ctl->nmax[h][1];
+            const int nchunk = ctl->nchunk[h];
+            for (int q = 0; q < nchunk; ++q) {
+                const int pa_q = ctl->cstart[h][q];
+                float4 G[kSW];
+#pragma unroll
+                for (int s = 0; s < kSW; ++s) G[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 *wp = &xt.w[pa_q];
+                uint32_t zp = strip + (uint32_t)pa_q * 512u;
+                const unsigned long long cnt = ctl->ccnt[h][q];
+                if (NX <= 2) bwd_col_pass<2>(G, cnt, wp, zp);
+                else if (NX == 3) bwd_col_pass<3>(G, cnt, wp, zp);
+                else bwd_col_pass<4>(G, cnt, wp, zp);
+                float *gp = grow_img + (size_t)ctl->cx0[h][q] * C;
+                const unsigned m = ctl->cmask[h][q];
+#pragma unroll
+                for (int s = 0; s < kSW; ++s)
+                    if (active && ((m >> s) & 1u)) red_add_v4(gp + (kC ? s * kC : s * C), G[s]);
             }
             __syncwarp();
         }
@@ -596,15 +639,16 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     build_tables(P, c, true, ctl);
     const int x0 = ctl->wmin[1], x1 = ctl->wmax[1];
     const int y0 = ctl->wmin[0], y1 = ctl->wmax[0];
-    if (!ctl->eligible || x1 - x0 >= kExt || y1 - y0 >= kExt) {
+    if (!ctl->eligible || y1 - y0 >= kExt || c.L.W < kSW) {
         generic_backward(P);
         return;
     }
     if (x1 < x0 || y1 < y0) return;
+    build_chunks(P, c, ctl, kPMax);
     build_ttabs(P, ctl, tt);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t strip = smem_u32(smem_raw + kCtlBytes + P.n_heads * 2 * kTTabBytes) +
+    const uint32_t strip = smem_u32(smem_raw + kCtlBytes + P.n_heads * kTTabBytes) +
                            (uint32_t)warp * (uint32_t)P.strip_cols * 512u + (uint32_t)lane * 16u;
     bool exact = (P.C == 256);
     for (int h = 0; h < P.n_heads; ++h) exact = exact && (P.PW[h] % kZ == 0);
