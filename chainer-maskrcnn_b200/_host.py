@@ -42,3 +42,24 @@ def d2h(t):
 
 def pinned_empty(shape, dtype=torch.float32):
     return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
+def d2h_async(t):
+    """Starts the copy of a CUDA tensor into a pinned buffer of the same strides on
+    the current stream; the caller synchronises that stream before reading
+    ``.numpy()`` of the returned tensor."""
+    host = torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    return host
+
+
+_COPY_STREAMS = {}
+
+
+def copy_streams(dev):
+    """(upload, download) side streams of a device: the two copy engines run
+    concurrently with each other and with the kernels on the caller's stream."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = (torch.cuda.Stream(device=key), torch.cuda.Stream(device=key))
+    return _COPY_STREAMS[key]

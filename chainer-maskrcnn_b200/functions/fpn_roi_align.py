@@ -47,22 +47,54 @@ def fpn_roi_align_host(x, indices_and_rois, levels, spatial_scales, out_sizes,
     every array is copied to the GPU, pooled there and copied back.  With ``gys``
     (one upstream gradient per pooled size) the backward pass runs too.
 
+    The three phases overlap on the two copy engines: the pooled maps travel back
+    while the upstream gradients travel in, and the kernels run on the caller's
+    stream in between.  Page-locked inputs are copied from where they lie; pageable
+    ones go through a pinned bounce buffer.
+
     Returns (pooled_list, grads_list_or_None) of NumPy arrays with the
-    reference's logical shapes."""
+    reference's logical shapes (channels-last strides, pinned memory)."""
     single = not isinstance(out_sizes, list)
     sizes = [out_sizes] if single else out_sizes
-    feats = [_host.h2d(f) for f in x]
-    rois = _host.h2d(indices_and_rois)
-    lv = None
-    if levels is not None:
-        lv = _host.h2d(levels, dtype=levels.dtype if levels.dtype.kind == "i" else "float32")
-        if lv.dtype not in (torch.int32, torch.float32):
-            lv = lv.to(torch.int32)
+    dev = _host.device()
+    cur = torch.cuda.current_stream(dev)
+    s_in, s_out = _host.copy_streams(dev)
+
+    def keep(t, *streams):          # tensors cross streams: tell the caching allocator
+        for st in streams:
+            t.record_stream(st)
+        return t
+
+    s_in.wait_stream(cur)
+    with torch.cuda.stream(s_in):
+        feats = [keep(_host.h2d(f, dev=dev), cur) for f in x]
+        rois = keep(_host.h2d(indices_and_rois, dev=dev), cur)
+        lv = None
+        if levels is not None:
+            lv = _host.h2d(levels, dtype=levels.dtype if levels.dtype.kind == "i" else "float32", dev=dev)
+            if lv.dtype not in (torch.int32, torch.float32):
+                lv = lv.to(torch.int32)
+            keep(lv, cur)
+        up1 = s_in.record_event()
+        g_dev, up2 = None, None
+        if gys is not None:
+            g_dev = [keep(_host.h2d(g, dev=dev), cur) for g in gys]
+            up2 = s_in.record_event()
+    cur.wait_event(up1)
     outs, plan = _engine.forward(feats, rois, lv, list(spatial_scales), sizes,
                                  sampling_ratio=sampling_ratio, roi_format=_lib.ROI_YX)
-    pooled = [_host.d2h(o) for o in outs]
+    s_out.wait_event(cur.record_event())
+    with torch.cuda.stream(s_out):
+        pooled = [_host.d2h_async(keep(o, s_out)) for o in outs]
     grads = None
     if gys is not None:
-        g_dev = [_host.h2d(g) for g in gys]
-        grads = [_host.d2h(g) for g in _engine.backward(plan, g_dev)]
+        cur.wait_event(up2)
+        g = _engine.backward(plan, g_dev)
+        s_out.wait_event(cur.record_event())
+        with torch.cuda.stream(s_out):
+            grads = [_host.d2h_async(keep(t, s_out)) for t in g]
+    s_out.synchronize()
+    pooled = [t.numpy() for t in pooled]
+    if grads is not None:
+        grads = [t.numpy() for t in grads]
     return pooled, grads
