@@ -152,6 +152,7 @@ int fill_params(const rpool_problem *p, const Workspace &w, bool bwd, int thread
     const int ctl = (int)((sizeof(BlockCtl) + 127) & ~(size_t)127);
     const int warps = threads / 32;
     k.prefetch = g_prefetch.load();
+    k.reverse = (bwd && g_order.load() == 1) ? 1 : 0;
     if (!bwd) return ctl;
     const int ttab = (int)((sizeof(TTab) + 127) & ~(size_t)127);
     k.strip_cols = sum_pw > 0 ? sum_pw : 1;
@@ -191,7 +192,7 @@ int rpool_set_tuning(const char *key, int value)
                         kMaxThreads);
         g_threads = value;
     } else if (!strcmp(key, "order")) {
-        if (value < 0 || value > 2) return fail(RPOOL_ERR_INVALID, "order=%d outside [0,2]", value);
+        if (value < 0 || value > 3) return fail(RPOOL_ERR_INVALID, "order=%d outside [0,3]", value);
         g_order = value;
     } else if (!strcmp(key, "force_path")) {
         if (value < 0 || value > 2) return fail(RPOOL_ERR_INVALID, "force_path=%d outside [0,2]", value);

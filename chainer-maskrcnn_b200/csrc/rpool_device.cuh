@@ -49,6 +49,7 @@ struct KParams {
     int S;
     int mode;
     int strip_cols;  // backward: entries of a warp's strip (512 bytes each)
+    int reverse;     // walk the schedule backwards (set for the backward launch)
     int prefetch;    // backward: L2 prefetch distance in CTAs (0 = own RoI, < 0 = off)
     int force_path;
 };

@@ -42,7 +42,9 @@ __device__ __forceinline__ AxisGeom axis_of(const KParams &P, const RoiCtx &c, b
 
 __device__ __forceinline__ void roi_prologue(const KParams &P, RoiCtx &c)
 {
-    c.r = P.order[blockIdx.x];
+    // the backward launch walks the schedule from its far end: coarse levels (the
+    // widest windows, the longest CTAs) first, short CTAs in the tail of the launch
+    c.r = P.order[P.reverse ? P.R - 1 - (int)blockIdx.x : (int)blockIdx.x];
     int lvl = P.roi_level[c.r];
     lvl = lvl < 0 ? 0 : (lvl >= P.n_levels ? P.n_levels - 1 : lvl);
     c.lvl = lvl;
@@ -617,7 +619,7 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
             int row = threadIdx.x;
             for (int h = 0; h < P.n_heads; ++h) {
                 if (row >= 0 && row < P.PH[h]) {
-                    const int r2 = P.order[nb];
+                    const int r2 = P.order[P.reverse ? P.R - 1 - nb : nb];
                     const size_t row_floats = (size_t)P.PW[h] * P.C;
                     prefetch_l2_bulk(P.pooled[h] + ((size_t)r2 * P.PH[h] + row) * row_floats,
                                      (unsigned)(row_floats * 4));
@@ -670,7 +672,7 @@ struct PlanParams {
     int k_min;
     int n_levels;
     int n_images;   // max over levels
-    int order_mode; // 0 identity, 1 (image, level asc), 2 (image, level desc)
+    int order_mode; // 0 identity, 1 (image, level asc), 2 (image, level desc), 3 (level desc, image)
     int *levels;    // out
     int *order;     // out
     int *keys;      // scratch
@@ -711,8 +713,9 @@ rpool_plan_kernel(const __grid_constant__ PlanParams p)
         lvl = lvl < 0 ? 0 : (lvl >= L ? L - 1 : lvl);  // maskrcnn.py:141
         p.levels[i] = lvl;
         int b = q.b < 0 ? 0 : (q.b >= p.n_images ? p.n_images - 1 : q.b);
-        const int lk = (p.order_mode == 2) ? (L - 1 - lvl) : lvl;
-        p.keys[i] = by_image ? b * L + lk : lk;
+        const int lk = (p.order_mode >= 2) ? (L - 1 - lvl) : lvl;
+        // mode 3: coarse levels (the widest windows, the longest CTAs) of every image first
+        p.keys[i] = !by_image ? lk : (p.order_mode == 3 ? lk * p.n_images + b : b * L + lk);
     }
     if (p.order_mode == 0) {
         for (int i = tid; i < p.R; i += kPlanThreads) p.order[i] = i;

@@ -308,7 +308,7 @@ def test_empty_invalid_batch_and_level_clipping():
 
 def test_schedule_is_stable_binning_and_rows_keep_input_order():
     rng, feats, rois, levels, scales = make_case(seed=13, C=8, per_img=500)
-    for order_mode in (0, 1, 2):
+    for order_mode in (0, 1, 2, 3):
         _lib.set_tuning(order=order_mode)
         outs, _, plan = run_fused(feats, rois, None, scales, [7])
         lv, order = _engine.read_plan(plan)
@@ -318,8 +318,10 @@ def test_schedule_is_stable_binning_and_rows_keep_input_order():
             want = np.arange(len(lv))
         elif order_mode == 1:
             want = np.argsort(img * 4 + lv, kind="stable")
-        else:
+        elif order_mode == 2:
             want = np.argsort(img * 4 + (3 - lv), kind="stable")
+        else:
+            want = np.argsort((3 - lv) * (img.max() + 1) + img, kind="stable")
         assert np.array_equal(order, want.astype(np.int32))
         # row r of the output is RoI r whatever the schedule (fpn_roi_mask_head.py:59-63)
         ref_out = oracle.fpn_forward(feats, rois, levels, scales, 7)
