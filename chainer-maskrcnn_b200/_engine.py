@@ -257,8 +257,24 @@ def backward(plan, gys, deterministic=False, out=None):
                          accumulate=False, deterministic=deterministic)
     L = _lib.lib()
     with torch.cuda.device(plan.device):
-        _lib.check(L.rpool_backward(ctypes.byref(prob), plan.workspace.data_ptr(),
-                                    plan.workspace.numel(), _stream()))
+        ws, ws_n = plan.workspace.data_ptr(), plan.workspace.numel()
+        if deterministic:
+            # the scratch holds one private window per RoI: its size depends on the
+            # RoIs and is computed on the device (this query synchronises the stream)
+            need = ctypes.c_size_t(0)
+            _lib.check(L.rpool_backward_det_bytes(ctypes.byref(prob), ws, ws_n, _stream(),
+                                                  ctypes.byref(need)))
+            scratch = torch.empty(need.value, dtype=torch.uint8, device=plan.device)
+            prob.det_workspace = scratch.data_ptr()
+            prob.det_workspace_bytes = need.value
+        _lib.check(L.rpool_backward(ctypes.byref(prob), ws, ws_n, _stream()))
+        if deterministic:
+            err = ctypes.c_int32(0)
+            _lib.check(L.rpool_det_status(ws, R, _stream(), ctypes.byref(err)))
+            if err.value:
+                raise _lib.RpoolError(_lib.UNSUPPORTED, "deterministic backward: some RoIs need the generic "
+                                      "kernel path (pooled size > 16, sampling grid > 4, window taller "
+                                      "than 64 rows or map narrower than 8 columns); status %d" % err.value)
     return grads
 
 

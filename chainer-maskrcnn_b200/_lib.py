@@ -17,6 +17,7 @@ ROI_XY, ROI_YX = 0, 1
 COORD_CHAINER, COORD_CAFFE2 = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_TABLE = 0, 1, 2
 
+UNSUPPORTED = 2
 _STATUS = {1: "invalid argument", 2: "unsupported", 3: "workspace", 4: "CUDA error"}
 
 
@@ -55,7 +56,9 @@ class Problem(ctypes.Structure):
                 ("sampling_ratio", ctypes.c_int32),
                 ("coord_mode", ctypes.c_int32),
                 ("accumulate", ctypes.c_int32),
-                ("deterministic", ctypes.c_int32)]
+                ("deterministic", ctypes.c_int32),
+                ("det_workspace", ctypes.c_void_p),
+                ("det_workspace_bytes", ctypes.c_size_t)]
 
 
 EXPORTS = [
@@ -63,6 +66,7 @@ EXPORTS = [
     "rpool_get_tuning", "rpool_level_thresholds", "rpool_assign_levels",
     "rpool_workspace_bytes", "rpool_problem_size", "rpool_plan", "rpool_forward", "rpool_backward",
     "rpool_read_plan", "rpool_nchw_to_nhwc", "rpool_nhwc_to_nchw",
+    "rpool_backward_det_bytes", "rpool_det_status",
 ]
 
 _lib = None
@@ -100,6 +104,8 @@ def lib():
     for name in ("rpool_plan", "rpool_forward", "rpool_backward"):
         getattr(L, name).argtypes = [pp, vp, ctypes.c_size_t, vp]
     L.rpool_read_plan.argtypes = [vp, i32, vp, vp, vp]
+    L.rpool_backward_det_bytes.argtypes = [pp, vp, ctypes.c_size_t, vp, ctypes.POINTER(ctypes.c_size_t)]
+    L.rpool_det_status.argtypes = [vp, i32, vp, ctypes.POINTER(i32)]
     for name in ("rpool_nchw_to_nhwc", "rpool_nhwc_to_nchw"):
         getattr(L, name).argtypes = [vp, vp, i32, i32, i32, i32, vp]
     for name in EXPORTS:

@@ -45,22 +45,34 @@ int cuda_fail(cudaError_t e, const char *what)
         if (e__ != cudaSuccess) return cuda_fail(e__, what); \
     } while (0)
 
-// workspace layout: [levels R][order R][keys R] int32
+// workspace layout (r = R rounded up to 32):
+//   int32  levels[r] order[r] keys[r] gstart[288] rects[4r]
+//   uint64 woff[r] sizes[r] det_total, then int32 det_err (+ padding)
+constexpr size_t kGstartInts = 288;  // kPlanMaxKeys + 1, padded
 struct Workspace {
-    int *levels, *order, *keys;
+    int *levels, *order, *keys, *gstart, *rects;
+    unsigned long long *woff, *sizes, *det_total;
+    int *det_err;
 };
+size_t ws_round(int R) { return ((size_t)(R > 0 ? R : 1) + 31) & ~(size_t)31; }
 size_t ws_bytes(int R)
 {
-    const size_t r = ((size_t)(R > 0 ? R : 1) + 31) & ~(size_t)31;
-    return 3 * r * sizeof(int);
+    const size_t r = ws_round(R);
+    return (3 * r + kGstartInts + 4 * r) * sizeof(int) + (2 * r + 1) * sizeof(unsigned long long) + 16;
 }
 Workspace ws_split(void *ws, int R)
 {
-    const size_t r = ((size_t)(R > 0 ? R : 1) + 31) & ~(size_t)31;
+    const size_t r = ws_round(R);
     Workspace w;
     w.levels = static_cast<int *>(ws);
     w.order = w.levels + r;
     w.keys = w.order + r;
+    w.gstart = w.keys + r;
+    w.rects = w.gstart + kGstartInts;
+    w.woff = reinterpret_cast<unsigned long long *>(w.rects + 4 * r);
+    w.sizes = w.woff + r;
+    w.det_total = w.sizes + r;
+    w.det_err = reinterpret_cast<int *>(w.det_total + 1);
     return w;
 }
 
@@ -153,6 +165,10 @@ int fill_params(const rpool_problem *p, const Workspace &w, bool bwd, int thread
     const int warps = threads / 32;
     k.prefetch = g_prefetch.load();
     k.reverse = (bwd && g_order.load() == 1) ? 1 : 0;
+    k.det = 0;
+    k.det_rects = w.rects;
+    k.det_woff = w.woff;
+    k.det_err = w.det_err;
     if (!bwd) return ctl;
     const int ttab = (int)((sizeof(TTab) + 127) & ~(size_t)127);
     k.strip_cols = sum_pw > 0 ? sum_pw : 1;
@@ -290,7 +306,7 @@ int rpool_plan(const rpool_problem *p, void *ws, size_t ws_size, void *stream)
     for (int l = 0; l < p->n_levels; ++l) nimg = p->level[l].n_images > nimg ? p->level[l].n_images : nimg;
     k.n_images = nimg;
     k.order_mode = g_order.load();
-    k.levels = w.levels; k.order = w.order; k.keys = w.keys;
+    k.levels = w.levels; k.order = w.order; k.keys = w.keys; k.gstart = w.gstart;
     rpool_plan_kernel<<<1, kPlanThreads, 0, static_cast<cudaStream_t>(stream)>>>(k);
     CUDA_TRY(cudaGetLastError(), "rpool_plan_kernel launch");
     g_launches++;
@@ -316,13 +332,133 @@ int rpool_forward(const rpool_problem *p, void *ws, size_t ws_size, void *stream
     return RPOOL_OK;
 }
 
+// Launches the two prepass kernels of the deterministic backward (window
+// rectangles, offsets of the private windows).
+static int det_prepass(const rpool_problem *p, void *ws, cudaStream_t st, KParams &k, int &threads)
+{
+    if (g_order.load() != 1)
+        return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward needs the (image, level) schedule (order=1)");
+    if (p->feat_layout != RPOOL_NHWC || p->pool_layout != RPOOL_NHWC || (p->channels & 3) || p->channels > 128 * kGatherSlabs)
+        return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward needs channels-last tensors with "
+                    "C %% 4 == 0 and C <= %d", 128 * kGatherSlabs);
+    int nimg = 1;
+    for (int l = 0; l < p->n_levels; ++l) nimg = p->level[l].n_images > nimg ? p->level[l].n_images : nimg;
+    if (nimg * p->n_levels > kPlanMaxKeys)
+        return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward: images x levels = %d exceeds %d",
+                    nimg * p->n_levels, kPlanMaxKeys);
+    const Workspace w = ws_split(ws, p->n_rois);
+    threads = g_threads.load();
+    fill_params(p, w, true, threads, k);
+    k.reverse = 0;
+    CUDA_TRY(cudaMemsetAsync(w.det_err, 0, sizeof(int), st), "cudaMemsetAsync(det_err)");
+    if (p->n_rois > 0) {
+        rpool_det_rects_kernel<<<(p->n_rois + 127) / 128, 128, 0, st>>>(k, w.rects, w.sizes, w.det_err);
+        CUDA_TRY(cudaGetLastError(), "rpool_det_rects_kernel launch");
+        rpool_det_scan_kernel<<<1, 1024, 0, st>>>(w.order, w.sizes, p->n_rois, w.woff, w.det_total);
+        CUDA_TRY(cudaGetLastError(), "rpool_det_scan_kernel launch");
+        g_launches += 2;
+    } else {
+        CUDA_TRY(cudaMemsetAsync(w.det_total, 0, sizeof(unsigned long long), st), "cudaMemsetAsync(det_total)");
+    }
+    return RPOOL_OK;
+}
+
+int rpool_backward_det_bytes(const rpool_problem *p, void *ws, size_t ws_size, void *stream,
+                             size_t *bytes_out)
+{
+    int rc = validate(p, ws, ws_size, true);
+    if (rc) return rc;
+    if (!bytes_out) return fail(RPOOL_ERR_INVALID, "bytes_out is NULL");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    KParams k;
+    int threads;
+    rc = det_prepass(p, ws, st, k, threads);
+    if (rc) return rc;
+    const Workspace w = ws_split(ws, p->n_rois);
+    unsigned long long total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, w.det_total, sizeof(total), cudaMemcpyDeviceToHost, st), "copy det_total");
+    CUDA_TRY(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    *bytes_out = (size_t)total * sizeof(float) + 16;
+    return RPOOL_OK;
+}
+
+int rpool_det_status(void *ws, int32_t n_rois, void *stream, int32_t *err_out)
+{
+    if (!ws || !err_out || n_rois < 0) return fail(RPOOL_ERR_INVALID, "bad arguments");
+    const Workspace w = ws_split(ws, n_rois);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int e = 0;
+    CUDA_TRY(cudaMemcpyAsync(&e, w.det_err, sizeof(int), cudaMemcpyDeviceToHost, st), "copy det_err");
+    CUDA_TRY(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    *err_out = e;
+    return RPOOL_OK;
+}
+
+static int backward_det(const rpool_problem *p, void *ws, cudaStream_t st)
+{
+    if (!p->det_workspace) return fail(RPOOL_ERR_WORKSPACE, "deterministic backward: det_workspace is NULL "
+                                       "(size it with rpool_backward_det_bytes)");
+    if (reinterpret_cast<uintptr_t>(p->det_workspace) & 15)
+        return fail(RPOOL_ERR_INVALID, "det_workspace must be 16-byte aligned");
+    KParams k;
+    int threads;
+    int rc = det_prepass(p, ws, st, k, threads);
+    if (rc) return rc;
+    const Workspace w = ws_split(ws, p->n_rois);
+    k.det = 1;
+    k.det_scratch = static_cast<float *>(p->det_workspace);
+    k.det_scratch_floats = p->det_workspace_bytes / sizeof(float);
+    if (p->n_rois > 0) {
+        int smem = fill_params(p, w, true, threads, k);
+        while (smem > kMaxSmem && threads > 32) {
+            threads -= 32;
+            smem = fill_params(p, w, true, threads, k);
+        }
+        k.reverse = 0;
+        k.det = 1;
+        k.det_scratch = static_cast<float *>(p->det_workspace);
+        k.det_scratch_floats = p->det_workspace_bytes / sizeof(float);
+        rc = set_smem(rpool_backward_kernel, smem);
+        if (rc) return rc;
+        rpool_backward_kernel<<<p->n_rois, threads, smem, st>>>(k);
+        CUDA_TRY(cudaGetLastError(), "rpool_backward_kernel launch");
+        g_launches++;
+    }
+    GatherParams g;
+    memset(&g, 0, sizeof(g));
+    long long ctas = 0;
+    for (int l = 0; l < p->n_levels; ++l) {
+        g.lvl[l].data = static_cast<float *>(p->level[l].data);
+        g.lvl[l].n_images = p->level[l].n_images;
+        g.lvl[l].H = p->level[l].height;
+        g.lvl[l].W = p->level[l].width;
+        g.strips[l] = (p->level[l].width + kGatherCells - 1) / kGatherCells;
+        g.strip_base[l] = ctas;
+        ctas += (long long)p->level[l].n_images * p->level[l].height * g.strips[l];
+    }
+    g.strip_base[p->n_levels] = ctas;
+    if (ctas > 2147483647ll) return fail(RPOOL_ERR_UNSUPPORTED, "pyramid too large for the gather launch");
+    g.n_levels = p->n_levels;
+    g.C = p->channels;
+    g.accumulate = p->accumulate;
+    g.order = w.order; g.gstart = w.gstart; g.rects = w.rects; g.woff = w.woff;
+    g.scratch = static_cast<const float *>(p->det_workspace);
+    if (p->n_rois == 0) {
+        // no plan was made: every group is empty
+        CUDA_TRY(cudaMemsetAsync(w.gstart, 0, kGstartInts * sizeof(int), st), "cudaMemsetAsync(gstart)");
+    }
+    rpool_det_gather_kernel<<<(unsigned)ctas, kGatherCells * 32, 0, st>>>(g);
+    CUDA_TRY(cudaGetLastError(), "rpool_det_gather_kernel launch");
+    g_launches++;
+    return RPOOL_OK;
+}
+
 int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *stream)
 {
     int rc = validate(p, ws, ws_size, true);
     if (rc) return rc;
-    if (p->deterministic)
-        return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward is not implemented yet");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (p->deterministic) return backward_det(p, ws, st);
     if (!p->accumulate) {
         ZeroParams z;
         memset(&z, 0, sizeof(z));

@@ -50,6 +50,14 @@ struct KParams {
     int mode;
     int strip_cols;  // backward: entries of a warp's strip (512 bytes each)
     int reverse;     // walk the schedule backwards (set for the backward launch)
+    // deterministic backward: per-RoI window rectangles {x0,y0,x1,y1}, float offsets of
+    // their private windows in `det_scratch`, error flag (all in the plan workspace)
+    int det;
+    const int *det_rects;
+    const unsigned long long *det_woff;
+    float *det_scratch;
+    unsigned long long det_scratch_floats;
+    int *det_err;
     int prefetch;    // backward: L2 prefetch distance in CTAs (0 = own RoI, < 0 = off)
     int force_path;
 };
@@ -193,13 +201,15 @@ struct BlockCtl {
     unsigned long long mbar;
 };
 
-// Fills entry p of `t`; returns false when the footprint does not fit kNT cells.
-__device__ __forceinline__ bool fill_axis_entry(AxisTab &t, const AxisGeom &g, int mode, int p,
-                                                int &lo_out, int &hi_out)
+// Footprint of bin p along one axis: first cell, cell count (<= kNT), summed
+// weights.  Returns false when the footprint does not fit kNT cells.
+__device__ __forceinline__ bool axis_footprint(const AxisGeom &g, int mode, int p, int &lo_out,
+                                               int &n_out, float (&w)[kNT])
 {
-    float w[kNT] = {0.f, 0.f, 0.f, 0.f};
     int lo = 0, n = 0;
     bool ok = true;
+#pragma unroll
+    for (int k = 0; k < kNT; ++k) w[k] = 0.f;
     for (int s = 0; s < g.grid; ++s) {
         int i0, i1;
         float w0, w1;
@@ -219,6 +229,18 @@ __device__ __forceinline__ bool fill_axis_entry(AxisTab &t, const AxisGeom &g, i
         n = o1 + 1 > n ? o1 + 1 : n;
     }
     if (g.grid > kNT) ok = false;
+    lo_out = lo;
+    n_out = n;
+    return ok;
+}
+
+// Fills entry p of `t`; returns false when the footprint does not fit kNT cells.
+__device__ __forceinline__ bool fill_axis_entry(AxisTab &t, const AxisGeom &g, int mode, int p,
+                                                int &lo_out, int &hi_out)
+{
+    float w[kNT];
+    int lo, n;
+    const bool ok = axis_footprint(g, mode, p, lo, n, w);
     t.lo[p] = lo;
     t.n[p] = n;
     t.w[p] = make_float4(w[0], w[1], w[2], w[3]);
@@ -279,6 +301,18 @@ __device__ __forceinline__ float4 ldg_nc128(const float *p)
 __device__ __forceinline__ void red_add_v4(float *p, float4 v)
 {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ldg_cg128(const float *p)
+{
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stg128(float *p, float4 v)
+{
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ void red_add_f32(float *p, float v)

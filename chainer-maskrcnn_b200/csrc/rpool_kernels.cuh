@@ -40,11 +40,9 @@ __device__ __forceinline__ AxisGeom axis_of(const KParams &P, const RoiCtx &c, b
                 : make_axis(P.mode, bwd, c.box.y1, c.box.y2, c.L.scale, P.PH[h], P.S, c.L.H);
 }
 
-__device__ __forceinline__ void roi_prologue(const KParams &P, RoiCtx &c)
+__device__ __forceinline__ void roi_decode(const KParams &P, int slot, RoiCtx &c)
 {
-    // the backward launch walks the schedule from its far end: coarse levels (the
-    // widest windows, the longest CTAs) first, short CTAs in the tail of the launch
-    c.r = P.order[P.reverse ? P.R - 1 - (int)blockIdx.x : (int)blockIdx.x];
+    c.r = P.order[slot];
     int lvl = P.roi_level[c.r];
     lvl = lvl < 0 ? 0 : (lvl >= P.n_levels ? P.n_levels - 1 : lvl);
     c.lvl = lvl;
@@ -60,6 +58,13 @@ __device__ __forceinline__ void roi_prologue(const KParams &P, RoiCtx &c)
         ok = ok && ((reinterpret_cast<uintptr_t>(P.pooled[h]) & 15) == 0);
     }
     c.fast_ok = ok && (P.force_path != kPathGeneric);
+}
+
+__device__ __forceinline__ void roi_prologue(const KParams &P, RoiCtx &c)
+{
+    // the backward launch walks the schedule from its far end: coarse levels (the
+    // widest windows, the longest CTAs) first, short CTAs in the tail of the launch
+    roi_decode(P, P.reverse ? P.R - 1 - (int)blockIdx.x : (int)blockIdx.x, c);
 }
 
 // Builds the tables; returns with ctl fully populated and the CTA synchronised.
@@ -527,13 +532,14 @@ __device__ __forceinline__ void bwd_col_pass(float4 (&G)[kSW], unsigned long lon
 // no lane and no chunk position is ever masked.
 template <int kC, bool kExact>
 __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, const BlockCtl *ctl,
-                                          const TTab *tt, uint32_t strip)
+                                          const TTab *tt, uint32_t strip, float *det_win)
 {
     const int C = kC ? kC : P.C;
     const int slabs = (C + 127) >> 7;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int y0 = ctl->wmin[0];
+    const int y0 = ctl->wmin[0], x0 = ctl->wmin[1];
     const int Hc = ctl->wmax[0] - y0 + 1;
+    const int det_wc = ctl->wmax[1] - x0 + 1;
     float *img = c.L.data + (size_t)c.b * c.L.H * c.L.W * C;
 
     const int ntask = Hc * slabs;
@@ -591,11 +597,26 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
                 if (NX <= 2) bwd_col_pass<2>(G, cnt, wp, zp);
                 else if (NX == 3) bwd_col_pass<3>(G, cnt, wp, zp);
                 else bwd_col_pass<4>(G, cnt, wp, zp);
-                float *gp = grow_img + (size_t)ctl->cx0[h][q] * C;
                 const unsigned m = ctl->cmask[h][q];
+                if (det_win == nullptr) {
+                    float *gp = grow_img + (size_t)ctl->cx0[h][q] * C;
 #pragma unroll
-                for (int s = 0; s < kSW; ++s)
-                    if (active && ((m >> s) & 1u)) red_add_v4(gp + (kC ? s * kC : s * C), G[s]);
+                    for (int s = 0; s < kSW; ++s)
+                        if (active && ((m >> s) & 1u)) red_add_v4(gp + (kC ? s * kC : s * C), G[s]);
+                } else {
+                    // deterministic: plain read-modify-write of this RoI's private window
+                    // (this warp is the only writer of its row and slab; heads in order)
+                    float *gp = det_win + ((size_t)i * det_wc + (ctl->cx0[h][q] - x0)) * C + ch;
+#pragma unroll
+                    for (int s = 0; s < kSW; ++s) {
+                        if (active && ((m >> s) & 1u)) {
+                            float *a = gp + (kC ? s * kC : s * C);
+                            float4 v = ldg_cg128(a);
+                            v.x += G[s].x; v.y += G[s].y; v.z += G[s].z; v.w += G[s].w;
+                            stg128(a, v);
+                        }
+                    }
+                }
             }
             __syncwarp();
         }
@@ -635,17 +656,34 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     bool table_ok = c.fast_ok;
     for (int h = 0; h < P.n_heads; ++h) table_ok = table_ok && P.PH[h] <= kPBwd && P.PW[h] <= kPBwd;
     if (!table_ok) {
-        generic_backward(P);
+        if (P.det) { if (threadIdx.x == 0) atomicExch(P.det_err, 1); }   // no ordered generic path
+        else generic_backward(P);
         return;
     }
     build_tables(P, c, true, ctl);
     const int x0 = ctl->wmin[1], x1 = ctl->wmax[1];
     const int y0 = ctl->wmin[0], y1 = ctl->wmax[0];
     if (!ctl->eligible || y1 - y0 >= kExt || c.L.W < kSW) {
-        generic_backward(P);
+        if (P.det) { if (threadIdx.x == 0) atomicExch(P.det_err, 1); }
+        else generic_backward(P);
         return;
     }
     if (x1 < x0 || y1 < y0) return;
+    float *det_win = nullptr;
+    if (P.det) {
+        // this RoI's private window in the scratch buffer: zero it, then the tasks
+        // below add into it with plain stores
+        const int *rc = P.det_rects + 4 * (size_t)c.r;
+        const unsigned long long off = P.det_woff[c.r];
+        const unsigned long long n = (unsigned long long)(x1 - x0 + 1) * (y1 - y0 + 1) * P.C;
+        if (rc[0] != x0 || rc[1] != y0 || rc[2] != x1 || rc[3] != y1 || off + n > P.det_scratch_floats) {
+            if (threadIdx.x == 0) atomicExch(P.det_err, 2);
+            return;
+        }
+        det_win = P.det_scratch + off;
+        for (unsigned long long i = threadIdx.x * 4ull; i < n; i += blockDim.x * 4ull)
+            stg128(det_win + i, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
     build_chunks(P, c, ctl, kPMax);
     build_ttabs(P, ctl, tt);
 
@@ -654,8 +692,8 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
                            (uint32_t)warp * (uint32_t)P.strip_cols * 512u + (uint32_t)lane * 16u;
     bool exact = (P.C == 256);
     for (int h = 0; h < P.n_heads; ++h) exact = exact && (P.PW[h] % kZ == 0);
-    if (exact) bwd_tasks<256, true>(P, c, ctl, tt, strip);
-    else bwd_tasks<0, false>(P, c, ctl, tt, strip);
+    if (exact) bwd_tasks<256, true>(P, c, ctl, tt, strip, det_win);
+    else bwd_tasks<0, false>(P, c, ctl, tt, strip, det_win);
 }
 
 // ---------------------------------------------------------------------------
@@ -676,6 +714,7 @@ struct PlanParams {
     int *levels;    // out
     int *order;     // out
     int *keys;      // scratch
+    int *gstart;    // out: first schedule slot of every (image, level) key, [n_keys] = R
 };
 
 __device__ __forceinline__ int level_from_area(float y1, float x1, float y2, float x2,
@@ -719,6 +758,8 @@ rpool_plan_kernel(const __grid_constant__ PlanParams p)
     }
     if (p.order_mode == 0) {
         for (int i = tid; i < p.R; i += kPlanThreads) p.order[i] = i;
+        if (p.gstart)
+            for (int k = tid; k < kPlanMaxKeys + 1; k += kPlanThreads) p.gstart[k] = -1;
         return;
     }
     for (int i = tid; i < 32 * K; i += kPlanThreads) hist[i] = 0;
@@ -748,6 +789,10 @@ rpool_plan_kernel(const __grid_constant__ PlanParams p)
         }
     }
     __syncthreads();
+    if (p.gstart) {
+        for (int k = tid; k < kPlanMaxKeys + 1; k += kPlanThreads)
+            p.gstart[k] = (by_image && p.order_mode == 1) ? (k < K ? base[k] : p.R) : -1;
+    }
     for (int i0 = beg; i0 < end; i0 += 32) {
         const int i = i0 + lane;
         const bool active = i < end;
@@ -782,6 +827,193 @@ __global__ void rpool_levels_kernel(const __grid_constant__ LevelParams p)
     k = k > p.k_cap ? p.k_cap : k;
     if (p.out_f) p.out_f[i] = (float)k;
     if (p.out_i) p.out_i[i] = k;
+}
+
+// ---------------------------------------------------------------------------
+// deterministic backward: segmented reduction instead of atomics
+// ---------------------------------------------------------------------------
+// 1. rpool_det_rects_kernel   window rectangle of every RoI (same footprint
+//                             arithmetic as the pooling kernels) and its size;
+// 2. rpool_det_scan_kernel    exclusive scan of the sizes in schedule order ->
+//                             offset of each RoI's private window in the scratch;
+// 3. rpool_backward_kernel    (det = 1) writes each RoI's window contribution to
+//                             its private window: plain stores, one writer per cell;
+// 4. rpool_det_gather_kernel  every feature cell sums, in schedule order, the
+//                             windows that cover it and is written exactly once
+//                             (this also replaces the zero fill).
+// The summation order of every cell is fixed by the schedule, so results are
+// bit-identical from run to run.
+__global__ void rpool_det_rects_kernel(const __grid_constant__ KParams P, int *rects,
+                                       unsigned long long *sizes, int *err)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= P.R) return;
+    RoiCtx c;
+    roi_decode(P, slot, c);
+    int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -1, y1 = -1;
+    bool ok = c.fast_ok && c.L.W >= kSW;
+    for (int h = 0; h < P.n_heads; ++h) ok = ok && P.PH[h] <= kPBwd && P.PW[h] <= kPBwd;
+    if (c.valid && ok) {
+        for (int h = 0; h < P.n_heads; ++h) {
+            for (int axis = 0; axis < 2; ++axis) {
+                const AxisGeom g = axis_of(P, c, true, h, axis);
+                const int n_bins = axis ? P.PW[h] : P.PH[h];
+                for (int p = 0; p < n_bins; ++p) {
+                    int lo, n;
+                    float w[kNT];
+                    ok = axis_footprint(g, P.mode, p, lo, n, w) && ok;
+                    if (n > 0) {
+                        if (axis) { x0 = lo < x0 ? lo : x0; x1 = lo + n - 1 > x1 ? lo + n - 1 : x1; }
+                        else { y0 = lo < y0 ? lo : y0; y1 = lo + n - 1 > y1 ? lo + n - 1 : y1; }
+                    }
+                }
+            }
+        }
+        ok = ok && (y1 - y0 < kExt);
+    }
+    unsigned long long n = 0;
+    if (c.valid && !ok) atomicExch(err, 1);   // this RoI needs the generic path: not orderable
+    if (c.valid && ok && x1 >= x0 && y1 >= y0) n = (unsigned long long)(x1 - x0 + 1) * (y1 - y0 + 1) * P.C;
+    else { x0 = y0 = 0; x1 = y1 = -1; }
+    int *rc = rects + 4 * (size_t)c.r;
+    rc[0] = x0; rc[1] = y0; rc[2] = x1; rc[3] = y1;
+    sizes[slot] = n;
+}
+
+__global__ void __launch_bounds__(1024)
+rpool_det_scan_kernel(const int *__restrict__ order, const unsigned long long *__restrict__ sizes, int R,
+                      unsigned long long *woff, unsigned long long *total)
+{
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < R; base += 1024) {
+        const int i = base + tid;
+        const unsigned long long v = i < R ? sizes[i] : 0ull;
+        unsigned long long x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long s = wsum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, s, d);
+                if (lane >= d) s += y;
+            }
+            wsum[lane] = s;
+        }
+        __syncthreads();
+        const unsigned long long before = carry + (warp ? wsum[warp - 1] : 0ull) + x - v;
+        if (i < R) woff[order[i]] = before;
+        __syncthreads();
+        if (tid == 0) carry += wsum[31];
+        __syncthreads();
+    }
+    if (tid == 0) *total = carry;
+}
+
+struct GatherParams {
+    LevelDev lvl[kMaxLevels];
+    long long strip_base[kMaxLevels + 1];  // first CTA of every level
+    int strips[kMaxLevels];                // 8-cell strips per map row
+    int n_levels, C, accumulate;
+    const int *order, *gstart, *rects;
+    const unsigned long long *woff;
+    const float *scratch;
+};
+
+constexpr int kGatherCells = 8;   // cells (warps) per CTA
+constexpr int kGatherSlabs = 4;   // 128-channel slabs held in registers: C <= 512
+
+__global__ void __launch_bounds__(kGatherCells * 32)
+rpool_det_gather_kernel(const __grid_constant__ GatherParams p)
+{
+    __shared__ int s_x0[256], s_x1[256], s_y0[256], s_wc[256];
+    __shared__ unsigned long long s_off[256];
+    __shared__ int s_wcount[8], s_n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int l = 0;
+    while (l + 1 < p.n_levels && (long long)blockIdx.x >= p.strip_base[l + 1]) ++l;
+    const LevelDev L = p.lvl[l];
+    long long idx = (long long)blockIdx.x - p.strip_base[l];
+    const int sx = (int)(idx % p.strips[l]);
+    idx /= p.strips[l];
+    const int y = (int)(idx % L.H);
+    const int b = (int)(idx / L.H);
+    const int xs = sx * kGatherCells, x = xs + warp;
+    const int key = b * p.n_levels + l;
+    const int g0 = p.gstart[key], g1 = p.gstart[key + 1];
+    const int C = p.C;
+
+    float4 acc[kGatherSlabs];
+#pragma unroll
+    for (int k = 0; k < kGatherSlabs; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int batch = g0; batch < g1; batch += 256) {
+        // ordered compaction of the RoIs of this (image, level) whose window meets the strip
+        const int slot = batch + tid;
+        bool hit = false;
+        int rx0 = 0, rx1 = -1, ry0 = 0, ry1 = -1, r = 0;
+        if (slot < g1) {
+            r = p.order[slot];
+            const int4 rc = *reinterpret_cast<const int4 *>(p.rects + 4 * (size_t)r);
+            rx0 = rc.x; ry0 = rc.y; rx1 = rc.z; ry1 = rc.w;
+            hit = ry0 <= y && y <= ry1 && rx0 <= xs + kGatherCells - 1 && rx1 >= xs;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_wcount[warp] = __popc(m);
+        __syncthreads();
+        int pos = __popc(m & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) pos += s_wcount[w];
+        if (hit) {
+            s_x0[pos] = rx0; s_x1[pos] = rx1; s_y0[pos] = ry0; s_wc[pos] = rx1 - rx0 + 1;
+            s_off[pos] = p.woff[r];
+        }
+        if (tid == 0) {
+            int n = 0;
+            for (int w = 0; w < kGatherCells; ++w) n += s_wcount[w];
+            s_n = n;
+        }
+        __syncthreads();
+        const int n = s_n;
+        if (x < L.W) {
+            for (int e = 0; e < n; ++e) {
+                if (s_x0[e] <= x && x <= s_x1[e]) {
+                    const float *src = p.scratch + s_off[e] +
+                                       ((size_t)(y - s_y0[e]) * s_wc[e] + (x - s_x0[e])) * C + lane * 4;
+#pragma unroll
+                    for (int k = 0; k < kGatherSlabs; ++k) {
+                        if (k * 128 + lane * 4 < C) {
+                            const float4 v = ldg_nc128(src + k * 128);
+                            acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (x < L.W) {
+        float *dst = L.data + (((size_t)b * L.H + y) * L.W + x) * C + lane * 4;
+#pragma unroll
+        for (int k = 0; k < kGatherSlabs; ++k) {
+            if (k * 128 + lane * 4 < C) {
+                float4 v = acc[k];
+                if (p.accumulate) {
+                    const float4 o = *reinterpret_cast<const float4 *>(dst + k * 128);
+                    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                }
+                stg128(dst + k * 128, v);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -126,6 +126,10 @@ typedef struct rpool_problem {
     /* backward only */
     int32_t accumulate;    /* 0: gradients are zero-filled first; 1: += into them */
     int32_t deterministic; /* 0: atomics; 1: run-to-run reproducible summation     */
+    /* deterministic == 1 only: scratch for the per-RoI private windows, sized by
+     * rpool_backward_det_bytes (device memory, 16-byte aligned) */
+    void *det_workspace;
+    size_t det_workspace_bytes;
 } rpool_problem;
 
 RPOOL_API int rpool_version(void);
@@ -177,6 +181,19 @@ RPOOL_API int rpool_forward(const rpool_problem *problem, void *workspace, size_
  * applied to pooled[h] (= gy).  No gradient w.r.t. RoIs (roi_align_2d.py:190). */
 RPOOL_API int rpool_backward(const rpool_problem *problem, void *workspace, size_t workspace_bytes,
                    void *stream);
+
+/* Deterministic variant (problem->deterministic = 1): a segmented reduction.
+ * Every RoI writes its window contribution to a private window in
+ * det_workspace with plain stores, then every feature cell sums the windows that
+ * cover it in schedule order and is written exactly once (no atomics, no zero
+ * fill): bit-identical from run to run.  The scratch size depends on the RoIs:
+ * rpool_backward_det_bytes computes it on the device and SYNCHRONISES `stream`
+ * to return it.  RoIs that would need the generic kernel path
+ * cannot be ordered: they are skipped and flagged, query with rpool_det_status
+ * (0 = clean; synchronises `stream`). */
+RPOOL_API int rpool_backward_det_bytes(const rpool_problem *problem, void *workspace,
+                                       size_t workspace_bytes, void *stream, size_t *bytes_out);
+RPOOL_API int rpool_det_status(void *workspace, int32_t n_rois, void *stream, int32_t *err_out);
 
 /* Read back the schedule of the last plan (for tests): device->host copies of
  * the per-RoI level and the permutation; synchronises `stream`. */

@@ -109,9 +109,14 @@ def test_workspace_errors_without_gpu():
     assert L.rpool_forward(ctypes.byref(p), ws, 16, None) == 3
     assert L.rpool_workspace_bytes(1000) >= 3 * 4 * 1000
     assert L.rpool_plan(None, ws, 16, None) == 1
+    # the deterministic variant needs its scratch (sized by rpool_backward_det_bytes)
+    # and channels-last tensors
     p = _problem(deterministic=1)
-    ws = ctypes.create_string_buffer(4096)
-    assert L.rpool_backward(ctypes.byref(p), ws, 4096, None) == 2
+    ws = ctypes.create_string_buffer(8192)
+    assert L.rpool_backward(ctypes.byref(p), ws, 8192, None) == 3
+    assert b"det_workspace" in L.rpool_last_error()
+    p = _problem(deterministic=1, det_workspace=0x4000, det_workspace_bytes=1 << 20, feat_layout=1)
+    assert L.rpool_backward(ctypes.byref(p), ws, 8192, None) == 2
 
 
 def test_launch_without_gpu_fails_loudly():

@@ -44,7 +44,7 @@ def host(t):
 
 
 def run_fused(feats, rois_yx, levels, scales, out_sizes, S=1, mode=None, channels_last=True,
-              gys=None, levels_dtype=np.int32):
+              gys=None, levels_dtype=np.int32, deterministic=False):
     f = [dev(x, channels_last) for x in feats]
     lv = None if levels is None else dev(np.asarray(levels).astype(levels_dtype))
     outs, plan = _engine.forward(f, dev(rois_yx), lv, scales, out_sizes, sampling_ratio=S,
@@ -53,7 +53,8 @@ def run_fused(feats, rois_yx, levels, scales, out_sizes, S=1, mode=None, channel
         assert o.is_contiguous(memory_format=torch.channels_last) or o.numel() == 0 or o.shape[1] == 1
     grads = None
     if gys is not None:
-        grads = [host(g) for g in _engine.backward(plan, [dev(g) for g in gys])]
+        grads = [host(g) for g in _engine.backward(plan, [dev(g) for g in gys],
+                                                   deterministic=deterministic)]
     torch.cuda.synchronize()
     return [host(o) for o in outs], grads, plan
 
@@ -339,6 +340,46 @@ def test_forward_is_run_to_run_identical_and_backward_within_tolerance():
     assert np.array_equal(a[0], b[0])
     for x, y in zip(ga, gb):
         assert oracle.rel_err(x, y) <= BWD_TOL
+
+
+@pytest.mark.parametrize("mode_name,S,sizes", [("chainer", 1, [7, 14]), ("caffe2", 2, [14]),
+                                               ("caffe2", 2, [7, 14]), ("caffe2", 3, [5])])
+def test_deterministic_backward_is_bit_reproducible_and_matches_oracle(mode_name, S, sizes):
+    """problem.deterministic = 1: segmented reduction, no atomics.  Two runs agree bit
+    for bit (also with a different CTA size), and the result matches the oracle."""
+    rng, feats, rois, levels, scales = make_case(seed=21 + S, per_img=300)
+    mode = _lib.COORD_CHAINER if mode_name == "chainer" else _lib.COORD_CAFFE2
+    gys = [synth.make_gy(rng, rois.shape[0], feats[0].shape[1], P) for P in sizes]
+    _, ga, _ = run_fused(feats, rois, levels, scales, sizes, S, mode, gys=gys, deterministic=True)
+    _, gb, _ = run_fused(feats, rois, levels, scales, sizes, S, mode, gys=gys, deterministic=True)
+    _lib.set_tuning(threads=256)
+    _, gc, _ = run_fused(feats, rois, levels, scales, sizes, S, mode, gys=gys, deterministic=True)
+    _, want = oracle_fused(feats, rois, levels, scales, sizes, S, mode_name, gys)
+    for a, b, c, w in zip(ga, gb, gc, want):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+        assert oracle.rel_err(a, w) <= BWD_TOL
+
+
+def test_deterministic_backward_edge_cases():
+    rng, feats, rois, levels, scales = make_case(seed=31, C=8, per_img=20)
+    f = [dev(x, True) for x in feats]
+    # no RoIs: zero gradients, written by the gather kernel alone
+    outs, plan = _engine.forward(f, dev(rois[:0]), dev(levels[:0]), scales, [7])
+    grads = _engine.backward(plan, [dev(np.zeros((0, 8, 7, 7), np.float32))], deterministic=True)
+    assert all(float(g.abs().max()) == 0.0 for g in grads)
+    # a RoI of another image index and clipped levels behave as in the atomic kernel
+    r2 = rois.copy()
+    r2[3, 0] = 9
+    gy = synth.make_gy(rng, r2.shape[0], 8, 7)
+    outs, plan = _engine.forward(f, dev(r2), None, scales, [7], sampling_ratio=2)
+    ga = [host(g) for g in _engine.backward(plan, [dev(gy)])]
+    gd = [host(g) for g in _engine.backward(plan, [dev(gy)], deterministic=True)]
+    for a, d in zip(ga, gd):
+        assert oracle.rel_err(d, a) <= BWD_TOL
+    # pooled size 20 > 16 needs the generic path, which cannot be ordered: loud error
+    outs, plan = _engine.forward(f, dev(rois), None, scales, [20])
+    with pytest.raises(_lib.RpoolError):
+        _engine.backward(plan, [dev(synth.make_gy(rng, rois.shape[0], 8, 20))], deterministic=True)
 
 
 def test_layout_conversion_kernels():
