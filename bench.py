@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rois", type=int, default=0, help="0 = sized automatically")
+    ap.add_argument("--deterministic", action="store_true",
+                    help="time the deterministic (segmented reduction) backward instead of the atomic one")
     ap.add_argument("--tune", default="", help="comma list key=value for rpool_set_tuning")
     return ap.parse_args()
 
@@ -235,6 +237,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
     for kv in filter(None, args.tune.split(",")):
         k, v = kv.split("=")
@@ -261,7 +266,7 @@ def run_b200(args):
                                      roi_format=_lib.ROI_YX)
         if ev:
             ev[1].record()
-        _engine.backward(plan, gys, out=grads)
+        _engine.backward(plan, gys, out=grads, deterministic=args.deterministic)
         if ev:
             ev[2].record()
         return outs
@@ -373,7 +378,10 @@ def run_b200(args):
             "rois_per_gpu": R, "channels": C, "out_sizes": sizes, "sampling_ratio": S,
             "levels": "P2-P%d, assigned on device by the reference rule" % (cfg["n_levels"] + 1),
             "layout": "channels-last features/pooled/gradients resident in HBM",
-            "step": "rpool_plan + rpool_forward + rpool_backward (zero-fill included)",
+            "step": ("rpool_plan + rpool_forward + rpool_backward (deterministic: rectangles, scan, private "
+                     "windows, ordered gather; its scratch-size query synchronises once per step)"
+                     if args.deterministic else
+                     "rpool_plan + rpool_forward + rpool_backward (zero-fill included)"),
             "l2": "no flush: one step touches %.0f MB >> 126 MB L2"
                   % ((ab["O"] * 2 + ab["F"] * 2) / 1e6),
             "sharding": "by image, one process per GPU, no data-path collective",
