@@ -193,7 +193,7 @@ def make_plan(shapes, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
     plan.channels = int(C)
 
     L = _lib.lib()
-    ws_bytes = L.rpool_workspace_bytes(rois.shape[0])
+    ws_bytes = L.rpool_workspace_bytes_ex(rois.shape[0], len(plan.out_sizes), plan.coord_mode)
     plan.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=rois.device)
     # rpool_plan reads geometry only; level/pooled addresses are not dereferenced
     dummy = plan.workspace.data_ptr()

@@ -64,7 +64,7 @@ class Problem(ctypes.Structure):
 EXPORTS = [
     "rpool_version", "rpool_last_error", "rpool_launch_count", "rpool_set_tuning",
     "rpool_get_tuning", "rpool_level_thresholds", "rpool_assign_levels",
-    "rpool_workspace_bytes", "rpool_problem_size", "rpool_plan", "rpool_forward", "rpool_backward",
+    "rpool_workspace_bytes", "rpool_workspace_bytes_ex", "rpool_problem_size", "rpool_plan", "rpool_forward", "rpool_backward",
     "rpool_read_plan", "rpool_nchw_to_nhwc", "rpool_nhwc_to_nchw",
     "rpool_backward_det_bytes", "rpool_det_status",
 ]
@@ -100,6 +100,8 @@ def lib():
                                       vp, vp, vp]
     L.rpool_workspace_bytes.argtypes = [i32]
     L.rpool_workspace_bytes.restype = ctypes.c_size_t
+    L.rpool_workspace_bytes_ex.argtypes = [i32, i32, i32]
+    L.rpool_workspace_bytes_ex.restype = ctypes.c_size_t
     L.rpool_problem_size.restype = ctypes.c_size_t
     for name in ("rpool_plan", "rpool_forward", "rpool_backward"):
         getattr(L, name).argtypes = [pp, vp, ctypes.c_size_t, vp]
@@ -110,7 +112,7 @@ def lib():
         getattr(L, name).argtypes = [vp, vp, i32, i32, i32, i32, vp]
     for name in EXPORTS:
         if name not in ("rpool_last_error", "rpool_launch_count", "rpool_workspace_bytes",
-                        "rpool_problem_size"):
+                        "rpool_workspace_bytes_ex", "rpool_problem_size"):
             getattr(L, name).restype = ctypes.c_int
     if L.rpool_problem_size() != ctypes.sizeof(Problem):
         raise RuntimeError("rpool_problem layout mismatch: library %d bytes, binding %d bytes"

@@ -47,20 +47,32 @@ int cuda_fail(cudaError_t e, const char *what)
 
 // workspace layout (r = R rounded up to 32):
 //   int32  levels[r] order[r] keys[r] gstart[288] rects[4r]
-//   uint64 woff[r] sizes[r] det_total, then int32 det_err (+ padding)
+//   uint64 woff[r] sizes[r] det_total, then int32 det_err (+ padding to 16 bytes)
+//   RoI records (rpool_tables_kernel): one set of r records of rec_bytes(n_heads)
+//   for the forward geometry, and for RPOOL_COORD_CHAINER -- whose backward
+//   coordinates round differently (roi_align_2d.py:164-165) -- a second set
 constexpr size_t kGstartInts = 288;  // kPlanMaxKeys + 1, padded
 struct Workspace {
     int *levels, *order, *keys, *gstart, *rects;
     unsigned long long *woff, *sizes, *det_total;
     int *det_err;
+    unsigned char *recs_fwd, *recs_bwd;
+    int rec_stride;
 };
 size_t ws_round(int R) { return ((size_t)(R > 0 ? R : 1) + 31) & ~(size_t)31; }
-size_t ws_bytes(int R)
+size_t ws_fixed_bytes(int R)
 {
     const size_t r = ws_round(R);
-    return (3 * r + kGstartInts + 4 * r) * sizeof(int) + (2 * r + 1) * sizeof(unsigned long long) + 16;
+    const size_t n = (3 * r + kGstartInts + 4 * r) * sizeof(int) + (2 * r + 1) * sizeof(unsigned long long) + 16;
+    return (n + 15) & ~(size_t)15;
 }
-Workspace ws_split(void *ws, int R)
+int rec_sets(int coord_mode) { return coord_mode == RPOOL_COORD_CHAINER ? 2 : 1; }
+size_t ws_bytes_ex(int R, int n_heads, int coord_mode)
+{
+    return ws_fixed_bytes(R) + (size_t)rec_sets(coord_mode) * (size_t)(R > 0 ? R : 0) * (size_t)rec_bytes(n_heads);
+}
+size_t ws_bytes(int R) { return ws_bytes_ex(R, RPOOL_MAX_HEADS, RPOOL_COORD_CHAINER); }
+Workspace ws_split(void *ws, int R, int n_heads, int coord_mode)
 {
     const size_t r = ws_round(R);
     Workspace w;
@@ -73,7 +85,14 @@ Workspace ws_split(void *ws, int R)
     w.sizes = w.woff + r;
     w.det_total = w.sizes + r;
     w.det_err = reinterpret_cast<int *>(w.det_total + 1);
+    w.rec_stride = rec_bytes(n_heads);
+    w.recs_fwd = static_cast<unsigned char *>(ws) + ws_fixed_bytes(R);
+    w.recs_bwd = rec_sets(coord_mode) == 2 ? w.recs_fwd + (size_t)(R > 0 ? R : 0) * (size_t)w.rec_stride : w.recs_fwd;
     return w;
+}
+Workspace ws_split(void *ws, const rpool_problem *p)
+{
+    return ws_split(ws, p->n_rois, p->n_heads, p->coord_mode);
 }
 
 int validate(const rpool_problem *p, void *ws, size_t ws_size, bool need_pooled)
@@ -123,9 +142,10 @@ int validate(const rpool_problem *p, void *ws, size_t ws_size, bool need_pooled)
             return fail(RPOOL_ERR_INVALID, "n_thresholds=%d", p->n_thresholds);
     }
     if (!ws) return fail(RPOOL_ERR_WORKSPACE, "workspace is NULL");
-    if (ws_size < ws_bytes(p->n_rois))
+    if (reinterpret_cast<uintptr_t>(ws) & 15) return fail(RPOOL_ERR_WORKSPACE, "workspace must be 16-byte aligned");
+    if (ws_size < ws_bytes_ex(p->n_rois, p->n_heads, p->coord_mode))
         return fail(RPOOL_ERR_WORKSPACE, "workspace has %zu bytes, %zu needed", ws_size,
-                    ws_bytes(p->n_rois));
+                    ws_bytes_ex(p->n_rois, p->n_heads, p->coord_mode));
     return RPOOL_OK;
 }
 
@@ -169,6 +189,8 @@ int fill_params(const rpool_problem *p, const Workspace &w, bool bwd, int thread
     k.det_rects = w.rects;
     k.det_woff = w.woff;
     k.det_err = w.det_err;
+    k.recs = bwd ? w.recs_bwd : w.recs_fwd;
+    k.rec_stride = w.rec_stride;
     if (!bwd) return ctl;
     const int ttab = (int)((sizeof(TTab) + 127) & ~(size_t)127);
     k.strip_cols = sum_pw > 0 ? sum_pw : 1;
@@ -285,6 +307,12 @@ int rpool_assign_levels(const float *boxes, int32_t n, int32_t box_stride, int32
 
 size_t rpool_workspace_bytes(int32_t n_rois) { return ws_bytes(n_rois); }
 
+size_t rpool_workspace_bytes_ex(int32_t n_rois, int32_t n_heads, int32_t coord_mode)
+{
+    if (n_heads < 1 || n_heads > RPOOL_MAX_HEADS) n_heads = RPOOL_MAX_HEADS;
+    return ws_bytes_ex(n_rois, n_heads, coord_mode);
+}
+
 size_t rpool_problem_size(void) { return sizeof(rpool_problem); }
 
 int rpool_plan(const rpool_problem *p, void *ws, size_t ws_size, void *stream)
@@ -292,7 +320,7 @@ int rpool_plan(const rpool_problem *p, void *ws, size_t ws_size, void *stream)
     int rc = validate(p, ws, ws_size, false);
     if (rc) return rc;
     if (p->n_rois == 0) return RPOOL_OK;
-    const Workspace w = ws_split(ws, p->n_rois);
+    const Workspace w = ws_split(ws, p);
     PlanParams k;
     memset(&k, 0, sizeof(k));
     k.rois = p->rois; k.R = p->n_rois; k.roi_format = p->roi_format;
@@ -310,6 +338,17 @@ int rpool_plan(const rpool_problem *p, void *ws, size_t ws_size, void *stream)
     rpool_plan_kernel<<<1, kPlanThreads, 0, static_cast<cudaStream_t>(stream)>>>(k);
     CUDA_TRY(cudaGetLastError(), "rpool_plan_kernel launch");
     g_launches++;
+    // every RoI's footprint tables and chunking, built once here (all RoIs in
+    // parallel) instead of in the prologue of every pooling CTA
+    for (int bwd = 0; bwd < rec_sets(p->coord_mode); ++bwd) {
+        KParams kp;
+        fill_params(p, w, bwd != 0, kTablesThreads, kp);
+        kp.reverse = 0;
+        rpool_tables_kernel<<<p->n_rois, kTablesThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+            kp, bwd, bwd ? w.recs_bwd : w.recs_fwd);
+        CUDA_TRY(cudaGetLastError(), "rpool_tables_kernel launch");
+        g_launches++;
+    }
     return RPOOL_OK;
 }
 
@@ -320,7 +359,7 @@ int rpool_forward(const rpool_problem *p, void *ws, size_t ws_size, void *stream
     if (p->n_rois == 0) return RPOOL_OK;
     KParams k;
     const int threads = g_threads.load();
-    const int smem = fill_params(p, ws_split(ws, p->n_rois), false, threads, k);
+    const int smem = fill_params(p, ws_split(ws, p), false, threads, k);
     if (smem > kMaxSmem)
         return fail(RPOOL_ERR_UNSUPPORTED, "forward needs %d bytes of shared memory; the limit is %d",
                     smem, kMaxSmem);
@@ -346,7 +385,7 @@ static int det_prepass(const rpool_problem *p, void *ws, cudaStream_t st, KParam
     if (nimg * p->n_levels > kPlanMaxKeys)
         return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward: images x levels = %d exceeds %d",
                     nimg * p->n_levels, kPlanMaxKeys);
-    const Workspace w = ws_split(ws, p->n_rois);
+    const Workspace w = ws_split(ws, p);
     threads = g_threads.load();
     fill_params(p, w, true, threads, k);
     k.reverse = 0;
@@ -374,7 +413,7 @@ int rpool_backward_det_bytes(const rpool_problem *p, void *ws, size_t ws_size, v
     int threads;
     rc = det_prepass(p, ws, st, k, threads);
     if (rc) return rc;
-    const Workspace w = ws_split(ws, p->n_rois);
+    const Workspace w = ws_split(ws, p);
     unsigned long long total = 0;
     CUDA_TRY(cudaMemcpyAsync(&total, w.det_total, sizeof(total), cudaMemcpyDeviceToHost, st), "copy det_total");
     CUDA_TRY(cudaStreamSynchronize(st), "cudaStreamSynchronize");
@@ -385,7 +424,7 @@ int rpool_backward_det_bytes(const rpool_problem *p, void *ws, size_t ws_size, v
 int rpool_det_status(void *ws, int32_t n_rois, void *stream, int32_t *err_out)
 {
     if (!ws || !err_out || n_rois < 0) return fail(RPOOL_ERR_INVALID, "bad arguments");
-    const Workspace w = ws_split(ws, n_rois);
+    const Workspace w = ws_split(ws, n_rois, 1, RPOOL_COORD_CAFFE2);   // fixed part only
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int e = 0;
     CUDA_TRY(cudaMemcpyAsync(&e, w.det_err, sizeof(int), cudaMemcpyDeviceToHost, st), "copy det_err");
@@ -404,7 +443,7 @@ static int backward_det(const rpool_problem *p, void *ws, cudaStream_t st)
     int threads;
     int rc = det_prepass(p, ws, st, k, threads);
     if (rc) return rc;
-    const Workspace w = ws_split(ws, p->n_rois);
+    const Workspace w = ws_split(ws, p);
     k.det = 1;
     k.det_scratch = static_cast<float *>(p->det_workspace);
     k.det_scratch_floats = p->det_workspace_bytes / sizeof(float);
@@ -481,10 +520,10 @@ int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *strea
     if (p->n_rois == 0) return RPOOL_OK;
     KParams k;
     int threads = g_threads.load();
-    int smem = fill_params(p, ws_split(ws, p->n_rois), true, threads, k);
+    int smem = fill_params(p, ws_split(ws, p), true, threads, k);
     while (smem > kMaxSmem && threads > 32) {  // two wide heads: fewer warps, same result
         threads -= 32;
-        smem = fill_params(p, ws_split(ws, p->n_rois), true, threads, k);
+        smem = fill_params(p, ws_split(ws, p), true, threads, k);
     }
     rc = set_smem(rpool_backward_kernel, smem);
     if (rc) return rc;
@@ -498,7 +537,7 @@ int rpool_read_plan(const void *ws, int32_t n_rois, int32_t *levels_host, int32_
                     void *stream)
 {
     if (!ws || n_rois < 0) return fail(RPOOL_ERR_INVALID, "bad arguments");
-    const Workspace w = ws_split(const_cast<void *>(ws), n_rois);
+    const Workspace w = ws_split(const_cast<void *>(ws), n_rois, 1, RPOOL_COORD_CAFFE2);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (levels_host)
         CUDA_TRY(cudaMemcpyAsync(levels_host, w.levels, sizeof(int) * n_rois, cudaMemcpyDeviceToHost, st),

@@ -27,7 +27,7 @@ namespace rpool {
 struct RoiCtx {
     int r, lvl, b;
     bool valid;       // batch index inside the level's tensor
-    bool fast_ok;     // layouts/alignment allow the table-driven paths at all
+    bool fast_ok;     // layouts, channel count, pooled sizes and map width allow the table paths
     LevelDev L;
     RoiBox box;
 };
@@ -52,51 +52,71 @@ __device__ __forceinline__ void roi_decode(const KParams &P, int slot, RoiCtx &c
     c.box = q;
     c.valid = (q.b >= 0 && q.b < c.L.n_images);
     bool ok = (P.feat_layout == RPOOL_NHWC) && (P.pool_layout == RPOOL_NHWC) && (P.C % 4 == 0);
-    ok = ok && ((reinterpret_cast<uintptr_t>(c.L.data) & 15) == 0);
-    for (int h = 0; h < P.n_heads; ++h) {
-        ok = ok && P.PH[h] <= kPMax && P.PW[h] <= kPMax;
-        ok = ok && ((reinterpret_cast<uintptr_t>(P.pooled[h]) & 15) == 0);
-    }
-    c.fast_ok = ok && (P.force_path != kPathGeneric);
+    for (int h = 0; h < P.n_heads; ++h) ok = ok && P.PH[h] <= kPMax && P.PW[h] <= kPMax;
+    // the table path reads spans of kSW columns: the map must be that wide
+    c.fast_ok = ok && c.L.W >= kSW;
+}
+
+__device__ __forceinline__ int launch_slot(const KParams &P)
+{
+    // the backward launch walks the schedule from its far end: coarse levels (the
+    // widest windows, the longest CTAs) first, short CTAs in the tail of the launch
+    return P.reverse ? P.R - 1 - (int)blockIdx.x : (int)blockIdx.x;
 }
 
 __device__ __forceinline__ void roi_prologue(const KParams &P, RoiCtx &c)
 {
-    // the backward launch walks the schedule from its far end: coarse levels (the
-    // widest windows, the longest CTAs) first, short CTAs in the tail of the launch
-    roi_decode(P, P.reverse ? P.R - 1 - (int)blockIdx.x : (int)blockIdx.x, c);
+    roi_decode(P, launch_slot(P), c);
 }
 
-// Builds the tables; returns with ctl fully populated and the CTA synchronised.
+// Copies this CTA's RoI record (header + n_heads head parts) from the workspace
+// into shared memory; returns with the CTA synchronised.
+__device__ __forceinline__ void load_record(const KParams &P, BlockCtl *ctl)
+{
+    const uint4 *src = reinterpret_cast<const uint4 *>(P.recs + (size_t)launch_slot(P) * P.rec_stride);
+    uint4 *dst = reinterpret_cast<uint4 *>(ctl);
+    const int n16 = rec_bytes(P.n_heads) >> 4;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+}
+
+// What the table path needs beyond the record: the tensors of this launch must
+// allow 128-bit accesses (the record was built from the geometry alone).
+__device__ __forceinline__ bool pointers_aligned(const KParams &P, const LevelDev &L)
+{
+    bool ok = (reinterpret_cast<uintptr_t>(L.data) & 15) == 0;
+    for (int h = 0; h < P.n_heads; ++h) ok = ok && ((reinterpret_cast<uintptr_t>(P.pooled[h]) & 15) == 0);
+    return ok;
+}
+
+// Builds the footprint tables of one RoI in `ctl` (any CTA size); returns with
+// the CTA synchronised.  Clears kRecFits when a footprint does not fit kNT cells.
 __device__ __forceinline__ void build_tables(const KParams &P, const RoiCtx &c, bool bwd, BlockCtl *ctl)
 {
     const int tid = threadIdx.x;
     if (tid == 0) {
         ctl->wmin[0] = ctl->wmin[1] = 0x7fffffff;
         ctl->wmax[0] = ctl->wmax[1] = -1;
-        ctl->eligible = 1;
-        for (int h = 0; h < kMaxHeads; ++h) ctl->nmax[h][0] = ctl->nmax[h][1] = 0;
+        for (int h = 0; h < kMaxHeads; ++h) ctl->hd[h].nmax[0] = ctl->hd[h].nmax[1] = 0;
     }
     __syncthreads();
+    int total = 0;
+    for (int h = 0; h < P.n_heads; ++h) total += P.PH[h] + P.PW[h];
     // entry e -> (head, axis, bin)
-    int base = 0;
-    for (int h = 0; h < P.n_heads; ++h) {
-        const int ny = P.PH[h], nx = P.PW[h];
-        const int e = tid - base;
-        if (e >= 0 && e < ny + nx) {
-            const int axis = e < ny ? 0 : 1;
-            const int p = axis ? e - ny : e;
-            int lo, hi;
-            const bool ok = fill_axis_entry(ctl->tab[h][axis], axis_of(P, c, bwd, h, axis), P.mode,
-                                            p, lo, hi);
-            if (!ok) ctl->eligible = 0;
-            if (hi >= lo) {
-                atomicMin(&ctl->wmin[axis], lo);
-                atomicMax(&ctl->wmax[axis], hi);
-                atomicMax(&ctl->nmax[h][axis], hi - lo + 1);
-            }
+    for (int e0 = tid; e0 < total; e0 += blockDim.x) {
+        int h = 0, e = e0;
+        while (e >= P.PH[h] + P.PW[h]) { e -= P.PH[h] + P.PW[h]; ++h; }
+        const int ny = P.PH[h];
+        const int axis = e < ny ? 0 : 1;
+        const int p = axis ? e - ny : e;
+        int lo, hi;
+        const bool ok = fill_axis_entry(ctl->hd[h].tab[axis], axis_of(P, c, bwd, h, axis), P.mode, p, lo, hi);
+        if (!ok) atomicAnd(&ctl->flags, ~kRecFits);
+        if (hi >= lo) {
+            atomicMin(&ctl->wmin[axis], lo);
+            atomicMax(&ctl->wmax[axis], hi);
+            atomicMax(&ctl->hd[h].nmax[axis], hi - lo + 1);
         }
-        base += ny + nx;
     }
     __syncthreads();
 }
@@ -329,11 +349,11 @@ __device__ __forceinline__ void fwd_tasks(const KParams &P, const RoiCtx &c, con
         const int ch = (tt - ph * slabs) * 128 + lane * 4;
         const bool active = ch < C;
         const int PH = P.PH[h], PW = P.PW[h];
-        const AxisTab &yt = ctl->tab[h][0];
-        const AxisTab &xt = ctl->tab[h][1];
+        const AxisTab &yt = ctl->hd[h].tab[0];
+        const AxisTab &xt = ctl->hd[h].tab[1];
         float *out = P.pooled[h] + (((size_t)c.r * PH + ph) * PW) * C + ch;
         const int ny = yt.n[ph];
-        const int NX = ctl->nmax[h][1];
+        const int NX = ctl->hd[h].nmax[1];
         if (ny == 0 || NX == 0) {
             if (active)
                 for (int pw = 0; pw < PW; ++pw) stg_stream128(out + (size_t)pw * C, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -342,19 +362,21 @@ __device__ __forceinline__ void fwd_tasks(const KParams &P, const RoiCtx &c, con
         const float4 wy = yt.w[ph];
         // lanes past the last channel of a partial slab read channel 0 and store nothing
         const float *rowp = img + (size_t)yt.lo[ph] * row_stride + (active ? ch : 0);
-        const int nchunk = ctl->nchunk[h];
+        const int nchunk = ctl->hd[h].nchunk;
         for (int q = 0; q < nchunk; ++q) {
-            const int pa = ctl->cstart[h][q];
-            const unsigned long long cnt = ctl->ccnt[h][q];
-            const float *p = rowp + (size_t)ctl->cx0[h][q] * C;
+            const int pa = ctl->hd[h].cstart[q];
+            const unsigned long long cnt = ctl->hd[h].ccnt[q];
+            const float *p = rowp + (size_t)ctl->hd[h].cx0[q] * C;
+            // rows 0 and 1 of the footprint are requested together (16 loads in flight,
+            // one exposed wait); a one-row footprint re-reads row 0 with weight zero
             float4 V[kSW], tmp[kSW];
-            fwd_load_row<kC>(tmp, p, C);
+            fwd_load_row<kC>(V, p, C);
+            fwd_load_row<kC>(tmp, p + (ny > 1 ? row_stride : 0), C);
+            const float wy1 = ny > 1 ? wy.y : 0.f;
 #pragma unroll
-            for (int s = 0; s < kSW; ++s) V[s] = mul4(wy.x, tmp[s]);
-            if (ny > 1) {
-                fwd_load_row<kC>(tmp, p + row_stride, C);
-#pragma unroll
-                for (int s = 0; s < kSW; ++s) fma4(V[s], wy.y, tmp[s]);
+            for (int s = 0; s < kSW; ++s) {
+                V[s] = mul4(wy.x, V[s]);
+                fma4(V[s], wy1, tmp[s]);
             }
             if (ny > 2) {
                 fwd_load_row<kC>(tmp, p + 2 * (size_t)row_stride, C);
@@ -383,14 +405,14 @@ __device__ __forceinline__ void build_chunks(const KParams &P, const RoiCtx &c, 
 {
     if (threadIdx.x < P.n_heads) {
         const int h = threadIdx.x;
-        const AxisTab &xt = ctl->tab[h][1];
+        const AxisTab &xt = ctl->hd[h].tab[1];
         const int PW = P.PW[h];
         const int W = c.L.W;
-        int NX = ctl->nmax[h][1];
+        int NX = ctl->hd[h].nmax[1];
         NX = NX < 1 ? 1 : NX;
         int n = 0, pa = 0;
         while (pa < PW) {
-            ctl->cstart[h][n] = (unsigned char)pa;
+            ctl->hd[h].cstart[n] = (unsigned char)pa;
             const int lo_a = xt.lo[pa];
             int x0 = lo_a < W - kSW ? lo_a : W - kSW;   // span [x0, x0 + kSW) inside the image
             x0 = x0 < 0 ? 0 : x0;
@@ -405,16 +427,50 @@ __device__ __forceinline__ void build_chunks(const KParams &P, const RoiCtx &c, 
                 mask |= ((1u << xt.n[pb]) - 1u) << (xt.lo[pb] - x0);
                 ++pb;
             }
-            ctl->cx0[h][n] = x0;
-            ctl->ccnt[h][n] = cnt;
-            ctl->cmask[h][n] = (unsigned char)(mask & 0xffu);
+            ctl->hd[h].cx0[n] = x0;
+            ctl->hd[h].ccnt[n] = cnt;
+            ctl->hd[h].cmask[n] = (unsigned char)(mask & 0xffu);
             ++n;
             pa = pb;
         }
-        ctl->cstart[h][n] = (unsigned char)PW;
-        ctl->nchunk[h] = n;
+        ctl->hd[h].cstart[n] = (unsigned char)PW;
+        ctl->hd[h].nchunk = n;
     }
     __syncthreads();
+}
+
+// Builds every RoI's record (footprint tables + chunking) for one direction:
+// one small CTA per schedule slot, all RoIs in parallel, once per plan.
+constexpr int kTablesThreads = 64;
+__global__ void __launch_bounds__(kTablesThreads)
+rpool_tables_kernel(const __grid_constant__ KParams P, int bwd, unsigned char *recs)
+{
+    __shared__ __align__(16) BlockCtl ctl_s;
+    BlockCtl *ctl = &ctl_s;
+    RoiCtx c;
+    roi_decode(P, blockIdx.x, c);
+    if (threadIdx.x == 0) {
+        ctl->r = c.r; ctl->lvl = c.lvl; ctl->b = c.b;
+        ctl->flags = (c.valid ? kRecValid : 0) | (c.fast_ok ? kRecShape : 0) | kRecFits;
+    }
+    if (c.valid && c.fast_ok) {      // (uniform) otherwise the consumer takes the generic path
+        build_tables(P, c, bwd != 0, ctl);
+        if (ctl->flags & kRecFits) build_chunks(P, c, ctl, kPMax);   // (uniform: read after the sync)
+    } else {
+        __syncthreads();
+    }
+    const uint4 *src = reinterpret_cast<const uint4 *>(ctl);
+    uint4 *dst = reinterpret_cast<uint4 *>(recs + (size_t)blockIdx.x * P.rec_stride);
+    const int n16 = rec_bytes(P.n_heads) >> 4;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+}
+
+__device__ __forceinline__ void ctx_from_record(const KParams &P, const BlockCtl *ctl, RoiCtx &c)
+{
+    c.r = ctl->r; c.lvl = ctl->lvl; c.b = ctl->b;
+    c.L = P.lvl[c.lvl];
+    c.valid = (ctl->flags & kRecValid) != 0;
+    c.fast_ok = (ctl->flags & kRecShape) != 0;
 }
 
 __global__ void __launch_bounds__(kMaxThreads, RPOOL_MIN_BLOCKS)
@@ -423,19 +479,14 @@ rpool_forward_kernel(const __grid_constant__ KParams P)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockCtl *ctl = reinterpret_cast<BlockCtl *>(smem_raw);
 
+    load_record(P, ctl);
     RoiCtx c;
-    roi_prologue(P, c);
-    // the table path reads spans of kSW columns: the map must be that wide
-    if (!c.fast_ok || !c.valid || c.L.W < kSW) {
+    ctx_from_record(P, ctl, c);
+    const int need = kRecValid | kRecShape | kRecFits;
+    if ((ctl->flags & need) != need || P.force_path == kPathGeneric || !pointers_aligned(P, c.L)) {
         generic_forward(P);
         return;
     }
-    build_tables(P, c, false, ctl);
-    if (!ctl->eligible) {
-        generic_forward(P);
-        return;
-    }
-    build_chunks(P, c, ctl, kPMax);
     if (P.C == 256) fwd_tasks<256>(P, c, ctl);
     else fwd_tasks<0>(P, c, ctl);
 }
@@ -475,7 +526,7 @@ __device__ __forceinline__ void build_ttabs(const KParams &P, const BlockCtl *ct
     for (int h = 0; h < P.n_heads; ++h) {
         const int p = tid - base;
         if (p >= 0 && p < P.PH[h]) {
-            const AxisTab &t = ctl->tab[h][0];
+            const AxisTab &t = ctl->hd[h].tab[0];
             TTab &T = tt[h];
             const int n = t.n[p], row0 = t.lo[p] - ctl->wmin[0];
             const float4 w4 = t.w[p];
@@ -557,23 +608,37 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
             const float *gbase = P.pooled[h] + ((size_t)c.r * PH + pa) * PW * C + ch;
             const int gstep = PW * C;
             for (int pw0 = 0; pw0 < PW; pw0 += kZ) {
-                float4 Z[kZ];
-#pragma unroll
-                for (int k = 0; k < kZ; ++k) Z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 Z[kZ], v[kZ];
                 const float *g = gbase + (size_t)pw0 * C;
                 const float *wrow = &Ty.w[i][0];
-                for (int ph = pa; ph < pb; ++ph, g += gstep) {
-                    const float w = wrow[ph];
-                    float4 v[kZ];
+                auto load_bins = [&](float4 (&dst)[kZ], const float *src) {
 #pragma unroll
                     for (int k = 0; k < kZ; ++k) {
                         if (kExact) {
-                            v[k] = ldg_nc128(g + (kC ? k * kC : k * C));
+                            dst[k] = ldg_nc128(src + (kC ? k * kC : k * C));
                         } else {
-                            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (active && pw0 + k < PW) v[k] = ldg_nc128(g + (size_t)k * C);
+                            dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (active && pw0 + k < PW) dst[k] = ldg_nc128(src + (size_t)k * C);
                         }
                     }
+                };
+                // the first two covering bin rows are requested together (2 * kZ loads in
+                // flight, one exposed wait); a single covering row is re-read with weight 0
+                const bool two = pa + 1 < pb;
+                load_bins(Z, g);
+                load_bins(v, g + (two ? gstep : 0));
+                {
+                    const float w0 = wrow[pa], w1 = two ? wrow[pa + 1] : 0.f;
+#pragma unroll
+                    for (int k = 0; k < kZ; ++k) {
+                        Z[k] = mul4(w0, Z[k]);
+                        fma4(Z[k], w1, v[k]);
+                    }
+                }
+                g += 2 * (size_t)gstep;
+                for (int ph = pa + 2; ph < pb; ++ph, g += gstep) {
+                    const float w = wrow[ph];
+                    load_bins(v, g);
 #pragma unroll
                     for (int k = 0; k < kZ; ++k) fma4(Z[k], w, v[k]);
                 }
@@ -583,30 +648,30 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
             }
             __syncwarp();
             // ---- column pass: bins in order, span offsets static (as in the forward bin pass)
-            const AxisTab &xt = ctl->tab[h][1];
-            const int NX = ctl->nmax[h][1];
-            const int nchunk = ctl->nchunk[h];
+            const AxisTab &xt = ctl->hd[h].tab[1];
+            const int NX = ctl->hd[h].nmax[1];
+            const int nchunk = ctl->hd[h].nchunk;
             for (int q = 0; q < nchunk; ++q) {
-                const int pa_q = ctl->cstart[h][q];
+                const int pa_q = ctl->hd[h].cstart[q];
                 float4 G[kSW];
 #pragma unroll
                 for (int s = 0; s < kSW; ++s) G[s] = make_float4(0.f, 0.f, 0.f, 0.f);
                 const float4 *wp = &xt.w[pa_q];
                 uint32_t zp = strip + (uint32_t)pa_q * 512u;
-                const unsigned long long cnt = ctl->ccnt[h][q];
+                const unsigned long long cnt = ctl->hd[h].ccnt[q];
                 if (NX <= 2) bwd_col_pass<2>(G, cnt, wp, zp);
                 else if (NX == 3) bwd_col_pass<3>(G, cnt, wp, zp);
                 else bwd_col_pass<4>(G, cnt, wp, zp);
-                const unsigned m = ctl->cmask[h][q];
+                const unsigned m = ctl->hd[h].cmask[q];
                 if (det_win == nullptr) {
-                    float *gp = grow_img + (size_t)ctl->cx0[h][q] * C;
+                    float *gp = grow_img + (size_t)ctl->hd[h].cx0[q] * C;
 #pragma unroll
                     for (int s = 0; s < kSW; ++s)
                         if (active && ((m >> s) & 1u)) red_add_v4(gp + (kC ? s * kC : s * C), G[s]);
                 } else {
                     // deterministic: plain read-modify-write of this RoI's private window
                     // (this warp is the only writer of its row and slab; heads in order)
-                    float *gp = det_win + ((size_t)i * det_wc + (ctl->cx0[h][q] - x0)) * C + ch;
+                    float *gp = det_win + ((size_t)i * det_wc + (ctl->hd[h].cx0[q] - x0)) * C + ch;
 #pragma unroll
                     for (int s = 0; s < kSW; ++s) {
                         if (active && ((m >> s) & 1u)) {
@@ -650,21 +715,17 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
         }
     }
 
+    load_record(P, ctl);
     RoiCtx c;
-    roi_prologue(P, c);
+    ctx_from_record(P, ctl, c);
     if (!c.valid) return;
-    bool table_ok = c.fast_ok;
+    const int need = kRecShape | kRecFits;
+    bool table_ok = (ctl->flags & need) == need && P.force_path != kPathGeneric && pointers_aligned(P, c.L);
     for (int h = 0; h < P.n_heads; ++h) table_ok = table_ok && P.PH[h] <= kPBwd && P.PW[h] <= kPBwd;
-    if (!table_ok) {
-        if (P.det) { if (threadIdx.x == 0) atomicExch(P.det_err, 1); }   // no ordered generic path
-        else generic_backward(P);
-        return;
-    }
-    build_tables(P, c, true, ctl);
     const int x0 = ctl->wmin[1], x1 = ctl->wmax[1];
     const int y0 = ctl->wmin[0], y1 = ctl->wmax[0];
-    if (!ctl->eligible || y1 - y0 >= kExt || c.L.W < kSW) {
-        if (P.det) { if (threadIdx.x == 0) atomicExch(P.det_err, 1); }
+    if (!table_ok || y1 - y0 >= kExt) {
+        if (P.det) { if (threadIdx.x == 0) atomicExch(P.det_err, 1); }   // no ordered generic path
         else generic_backward(P);
         return;
     }
@@ -684,7 +745,6 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
         for (unsigned long long i = threadIdx.x * 4ull; i < n; i += blockDim.x * 4ull)
             stg128(det_win + i, make_float4(0.f, 0.f, 0.f, 0.f));
     }
-    build_chunks(P, c, ctl, kPMax);
     build_ttabs(P, ctl, tt);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -851,7 +911,7 @@ __global__ void rpool_det_rects_kernel(const __grid_constant__ KParams P, int *r
     RoiCtx c;
     roi_decode(P, slot, c);
     int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -1, y1 = -1;
-    bool ok = c.fast_ok && c.L.W >= kSW;
+    bool ok = c.fast_ok && P.force_path != kPathGeneric;
     for (int h = 0; h < P.n_heads; ++h) ok = ok && P.PH[h] <= kPBwd && P.PW[h] <= kPBwd;
     if (c.valid && ok) {
         for (int h = 0; h < P.n_heads; ++h) {

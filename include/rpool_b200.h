@@ -159,16 +159,24 @@ RPOOL_API int rpool_assign_levels(const float *boxes, int32_t n, int32_t box_str
                         int32_t k_min, int32_t k_cap,
                         float *levels_f32, int32_t *levels_i32, void *stream);
 
-/* Scratch needed by rpool_plan/forward/backward for up to n_rois RoIs. */
+/* Scratch needed by rpool_plan/forward/backward for up to n_rois RoIs (16-byte
+ * aligned device memory): schedule arrays plus one record per RoI (footprint
+ * tables, about 2 KB per head).  rpool_workspace_bytes is the bound for any
+ * problem; the _ex form is exact for a head count and rpool_coord_mode. */
 RPOOL_API size_t rpool_workspace_bytes(int32_t n_rois);
+RPOOL_API size_t rpool_workspace_bytes_ex(int32_t n_rois, int32_t n_heads, int32_t coord_mode);
 
 /* sizeof(rpool_problem) as compiled, so that FFI bindings can verify their
  * struct layout against the library's. */
 RPOOL_API size_t rpool_problem_size(void);
 
 /* Bins the RoIs by (image, level) into the launch schedule kept in `workspace`
- * (level of every RoI + a stable permutation).  Must precede forward/backward
- * on the same stream; a plan stays valid while rois/roi_levels are unchanged. */
+ * (level of every RoI + a stable permutation) and builds every RoI's footprint
+ * tables there (rpool_tables_kernel: all RoIs in parallel, once, instead of in
+ * every pooling CTA).  Reads the geometry only: level/pooled addresses are not
+ * dereferenced.  Must precede forward/backward on the same stream; a plan stays
+ * valid while rois/roi_levels, the level shapes and scales, the pooled sizes,
+ * sampling_ratio, coord_mode and the layouts are unchanged. */
 RPOOL_API int rpool_plan(const rpool_problem *problem, void *workspace, size_t workspace_bytes,
                void *stream);
 

@@ -94,9 +94,10 @@ def _problem(**kw):
 def test_validation_errors_without_gpu(kw, code):
     L = _lib.lib()
     p = _problem(**kw)
-    ws = ctypes.create_string_buffer(4096)
+    raw = ctypes.create_string_buffer(65536 + 16)
+    ws = ctypes.c_void_p((ctypes.addressof(raw) + 15) & ~15)
     for fn in (L.rpool_plan, L.rpool_forward, L.rpool_backward):
-        rc = fn(ctypes.byref(p), ws, 4096, None)
+        rc = fn(ctypes.byref(p), ws, 65536, None)
         assert rc == code, (fn.__name__, kw, L.rpool_last_error())
         assert len(L.rpool_last_error()) > 0
 
@@ -112,11 +113,18 @@ def test_workspace_errors_without_gpu():
     # the deterministic variant needs its scratch (sized by rpool_backward_det_bytes)
     # and channels-last tensors
     p = _problem(deterministic=1)
-    ws = ctypes.create_string_buffer(8192)
-    assert L.rpool_backward(ctypes.byref(p), ws, 8192, None) == 3
+    n = L.rpool_workspace_bytes_ex(p.n_rois, p.n_heads, p.coord_mode)
+    assert 0 < n <= L.rpool_workspace_bytes(p.n_rois)
+    raw = ctypes.create_string_buffer(n + 16)
+    ws = ctypes.c_void_p((ctypes.addressof(raw) + 15) & ~15)
+    assert L.rpool_backward(ctypes.byref(p), ws, n - 1, None) == 3
+    assert b"needed" in L.rpool_last_error()
+    assert L.rpool_backward(ctypes.byref(p), ctypes.c_void_p(ws.value + 4), n, None) == 3
+    assert b"aligned" in L.rpool_last_error()
+    assert L.rpool_backward(ctypes.byref(p), ws, n, None) == 3
     assert b"det_workspace" in L.rpool_last_error()
     p = _problem(deterministic=1, det_workspace=0x4000, det_workspace_bytes=1 << 20, feat_layout=1)
-    assert L.rpool_backward(ctypes.byref(p), ws, 8192, None) == 2
+    assert L.rpool_backward(ctypes.byref(p), ws, n, None) == 2
 
 
 def test_launch_without_gpu_fails_loudly():
