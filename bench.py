@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--gpu-baseline-rois", type=int, default=512)
     ap.add_argument("--cpu-sample-rois", type=int, default=0, help="0 = sized automatically")
     ap.add_argument("--deterministic", action="store_true",
                     help="time the deterministic (segmented reduction) backward instead of the atomic one")
@@ -187,6 +189,45 @@ def cpu_arm(cfg_id, S, sample_rois, repeats=1):
                 oracle.ref_caffe2_forward(feats[l], rois_xy[m], P, P, scales[l], max(S, 1))
         info["reference_cpp_forward_rois_per_s_1thread"] = n / (time.perf_counter() - t0)
     return info["value"], info
+
+
+def gpu_baseline_arm(cfg_id, sample_rois, device, repeats=3):
+    """Same-box GPU baseline: the reference's CuPy kernels restated in CUDA
+    (oracle/refgpu_baseline.cu) and dispatched per RoI like the reference's FPN
+    heads, on a bounded sample of the workload (its cost grows with the level
+    map, not with the RoI: every backward call touches a whole dense gradient)."""
+    import torch
+    from oracle import refgpu
+    import oracle
+    cfg, rng, shapes, rois, scales = workload(cfg_id, 0)
+    sample_rois = min(sample_rois, rois.shape[0])
+    sel = np.sort(np.random.RandomState(99).choice(rois.shape[0], sample_rois, replace=False))
+    sub = rois[sel]
+    levels = oracle.levels_for_pyramid(sub[:, 1:], cfg["n_levels"])
+    feats = [torch.randn(s, device=device, dtype=torch.float32) for s in shapes]
+    state = refgpu.FpnState(feats, scales)
+    rois_xy = torch.from_numpy(oracle.roi_yx_to_xy(sub)).to(device)
+    total_ms, ops = 0.0, 0
+    for P in cfg["out_sizes"]:
+        top = torch.empty((sample_rois, cfg["channels"], P, P), device=device)
+        gy = torch.rand_like(top) * 2 - 1
+        refgpu.fpn_step(state, rois_xy, levels, P, top, gy)       # warm-up
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(repeats):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            n_ops = refgpu.fpn_step(state, rois_xy, levels, P, top, gy)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        total_ms += best
+        ops += n_ops
+    return {"value": sample_rois / (total_ms * 1e-3), "unit": UNIT, "kind": "reference CuPy kernels restated "
+            "(oracle/refgpu_baseline.cu), per-RoI dispatch of fpn_roi_mask_head.py:57-63, sampling_ratio 1, "
+            "NCHW", "sample": "%d of %d RoIs of %s (seed 99)" % (sample_rois, rois.shape[0], cfg["name"]),
+            "ms": total_ms, "device_ops": ops}
 
 
 def run_reference(args):
@@ -369,6 +410,12 @@ def run_b200(args):
             _, cpu = cpu_arm(args.config, S, args.cpu_sample_rois, repeats=3)
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+    gpu_base = None
+    if world == 1 and not args.no_gpu_baseline:
+        try:
+            gpu_base = gpu_baseline_arm(args.config, args.gpu_baseline_rois, device)
+        except Exception as e:  # noqa: BLE001
+            gpu_base = {"value": None, "unit": UNIT, "kind": "failed: %r" % (e,)}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / K, "higher_is_better": True,
@@ -388,7 +435,7 @@ def run_b200(args):
             "tuning": {k: _lib.get_tuning(k) for k in ("prefetch", "threads", "order", "force_path")},
         },
         "fwd_ms": fwd_ms_max, "bwd_ms": bwd_ms_max,
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "roofline": roofline, "cpu_baseline": cpu, "gpu_baseline": gpu_base, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line))

@@ -154,3 +154,45 @@ def test_errors_are_loud():
         roi_align_2d(x, r[:, :4], 2, 2, 1.0)
     with pytest.raises(TypeError):
         roi_align_2d(x.cpu(), r, 2, 2, 1.0)
+
+
+@pytest.mark.gpu
+def test_restated_cupy_kernels_agree_with_the_numpy_reference():
+    """The same-box GPU baseline (oracle/refgpu_baseline.cu restates the reference's
+    CuPy kernels, roi_align_2d.py:100-144 / :196-279) must compute the reference's
+    op: forward within 1e-5 of the NumPy-path oracle; backward within 1e-4 on RoIs
+    whose taps never coincide (the CuPy backward drops coincident-cell taps,
+    :256-272, the NumPy backward does not)."""
+    from oracle import refgpu
+    rng = np.random.RandomState(5)
+    x = rng.standard_normal((2, 8, 40, 56)).astype(np.float32)
+    rois_yx = synth.make_rois(rng, 2, 24, 160, 224, size_range=(40.0, 150.0))
+    # keep boxes away from the border so that x1 = min(x0 + 1, W - 1) never clamps
+    rois_yx[:, 1:3] = np.maximum(rois_yx[:, 1:3], 8.0)
+    rois_yx[:, 3] = np.minimum(rois_yx[:, 3], 150.0)
+    rois_yx[:, 4] = np.minimum(rois_yx[:, 4], 214.0)
+    rois_xy = oracle.roi_yx_to_xy(rois_yx)
+    xd, rd = torch.from_numpy(x).cuda(), torch.from_numpy(rois_xy).cuda()
+    top = refgpu.forward(xd, rd, 7, 7, 0.25)
+    want = oracle.forward_chainer(x, rois_xy, 7, 7, 0.25)
+    # 2e-5: the CuPy kernel forms the bin centre in double ((ph + 0.5) * bin + start, :127-128),
+    # the NumPy path in float32 -- a 1-ulp coordinate difference
+    assert oracle.rel_err(top.cpu().numpy(), want) <= 2e-5
+    gy = rng.uniform(-1, 1, (rois_xy.shape[0], 8, 7, 7)).astype(np.float32)
+    gx = refgpu.backward(torch.from_numpy(gy).cuda(), rd, x.shape, 0.25)
+    want_g = oracle.backward_chainer(gy, rois_xy, x.shape, 0.25)
+    assert oracle.rel_err(gx.cpu().numpy(), want_g) <= 1e-4
+    # the per-RoI dispatch over a pyramid reproduces the batched calls
+    feats = [xd, torch.from_numpy(rng.standard_normal((2, 8, 20, 28)).astype(np.float32)).cuda()]
+    state = refgpu.FpnState(feats, [0.25, 0.125])
+    levels = (np.arange(rois_xy.shape[0]) % 2).astype(np.int32)
+    out = torch.empty((rois_xy.shape[0], 8, 7, 7), device="cuda")
+    ops = refgpu.fpn_step(state, rd, levels, 7, out, torch.from_numpy(gy).cuda())
+    torch.cuda.synchronize()
+    assert ops == rois_xy.shape[0] * 4
+    for l, sc in enumerate([0.25, 0.125]):
+        m = np.nonzero(levels == l)[0]
+        w = oracle.forward_chainer(feats[l].cpu().numpy(), rois_xy[m], 7, 7, sc)
+        assert oracle.rel_err(out[torch.from_numpy(m).cuda()].cpu().numpy(), w) <= 2e-5
+        wg = oracle.backward_chainer(gy[m], rois_xy[m], tuple(feats[l].shape), sc)
+        assert oracle.rel_err(state.grads[l].cpu().numpy(), wg) <= 1e-4
