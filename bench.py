@@ -73,6 +73,17 @@ def algorithmic_bytes(cfg, shapes, rois, levels, scales, S):
     return dict(O=O, F=F, U_bytes=U * C * 4, fwd=O + U * C * 4 + 20 * R, bwd=O + F + 20 * R)
 
 
+def ncu_traffic(cfg_id, S, kernels):
+    """DRAM bytes per launch of the named kernels from the committed ncu --set full
+    capture (profiles/ncu_traffic.json); None when that workload was not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)["cfg%d_S%d" % (cfg_id, S)]
+        return float(sum(t[k]["read"] + t[k]["write"] for k in kernels))
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -388,7 +399,11 @@ def run_b200(args):
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": ncu_traffic(args.config, S, ["rpool_zero_kernel", "rpool_backward_kernel"]
+                               if dom == "backward" else ["rpool_forward_kernel"]),
+        "traffic_source": "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, "
+                          "ncu --set full, per launch)",
+        "peak_source": peak_src,
         "kernel": ("rpool_zero_kernel + rpool_backward_kernel" if dom == "backward"
                    else "rpool_plan_kernel + rpool_forward_kernel"),
         "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms,
