@@ -20,7 +20,7 @@ std::atomic<unsigned long long> g_launches{0};
 constexpr int kMaxSmem = 227 * 1024;
 
 // tuning knobs (process-wide; experiments only)
-std::atomic<int> g_prefetch{-1};
+std::atomic<int> g_prefetch{-3};
 std::atomic<int> g_threads{128};
 std::atomic<int> g_order{1};
 std::atomic<int> g_force_path{kPathAuto};
@@ -221,8 +221,8 @@ int rpool_set_tuning(const char *key, int value)
 {
     if (!key) return fail(RPOOL_ERR_INVALID, "key is NULL");
     if (!strcmp(key, "prefetch")) {
-        if (value < -1 || value > 65536)
-            return fail(RPOOL_ERR_INVALID, "prefetch=%d outside [-1,65536]", value);
+        if (value < -17 || value > 65536)
+            return fail(RPOOL_ERR_INVALID, "prefetch=%d outside [-17,65536]", value);
         g_prefetch = value;
     } else if (!strcmp(key, "threads")) {
         if (value < 32 || value > kMaxThreads || value % 32)

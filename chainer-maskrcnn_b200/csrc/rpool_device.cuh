@@ -59,7 +59,8 @@ struct KParams {
     float *det_scratch;
     unsigned long long det_scratch_floats;
     int *det_err;
-    int prefetch;    // backward: L2 prefetch distance in CTAs (0 = own RoI, < 0 = off)
+    int prefetch;    // backward, L2 prefetch of gy: -1 off; -1-k row-ahead with a lead of k window rows
+                     // (default k = 2); >= 0 whole RoI of the CTA scheduled that many slots later
     const unsigned char *recs;  // per-slot RoI records (rpool_tables_kernel), rec_stride bytes apart
     int rec_stride;
     int force_path;

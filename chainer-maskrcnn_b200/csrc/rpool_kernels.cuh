@@ -504,8 +504,9 @@ rpool_forward_kernel(const __grid_constant__ KParams P)
 //                Like the forward bin pass it walks the bins in order with the span
 //                offsets static, accumulating G[kSW] in registers.
 // The transposed y table (dense, kExt x kPBwd) is built in shared memory from the
-// forward footprint table.  gy of the RoI that a later
-// CTA will handle is pulled into L2 with one bulk prefetch per bin row.
+// forward footprint table.  The gy bin rows a warp's next task is the first to need
+// are pulled into L2 with one bulk prefetch (TMA unit) per bin row while the column
+// pass of the current task runs.
 struct TTab {
     float w[kExt][kPBwd];
     int pa[kExt], pb[kExt];  // covering bins of row/column i: [pa, pb)
@@ -599,6 +600,30 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
         const int ch = (t - i * slabs) * 128 + lane * 4;
         const bool active = kExact || ch < C;
         float *grow_img = img + (size_t)(y0 + i) * c.L.W * C + ch;   // column 0 of the window row
+        bool ahead_done = false;
+        auto row_ahead = [&]() {
+            if (P.prefetch <= -2 && lane == 0 && t - i * slabs == 0) {
+                // row-ahead mode: pull the gy bin rows that window row i + lead is the first to
+                // need into L2 (one bulk prefetch per bin row: PW * C floats, contiguous), so
+                // that the row pass of that task finds them at L2 latency.  Short leads only:
+                // measured on cfg 1, lead 2 (this warp's next task) 0.2265 ms, lead 1 0.2287,
+                // lead 3 0.2378, none 0.2431, the whole RoI at CTA start 0.2559
+                const int lead = -P.prefetch - 1;
+                const int in = i + lead;
+                if (in < Hc) {
+                    for (int h = 0; h < P.n_heads; ++h) {
+                        const int pb_n = tt[h].pb[in];
+                        int pa_n = tt[h].pa[in];
+                        const int seen = tt[h].pb[in - 1];      // (in >= 1: lead >= 1)
+                        pa_n = pa_n < seen ? seen : pa_n;
+                        const size_t row_floats = (size_t)P.PW[h] * C;
+                        for (int ph = pa_n; ph < pb_n; ++ph)
+                            prefetch_l2_bulk(P.pooled[h] + ((size_t)c.r * P.PH[h] + ph) * row_floats,
+                                             (unsigned)(row_floats * 4));
+                    }
+                }
+            }
+        };
         for (int h = 0; h < P.n_heads; ++h) {
             const TTab &Ty = tt[h];
             const int PH = P.PH[h], PW = P.PW[h];
@@ -647,6 +672,9 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
                     if (kExact || pw0 + k < PW) sts128(strip + (uint32_t)(pw0 + k) * 512u, Z[k]);
             }
             __syncwarp();
+            // (issued once this task's own gy loads have landed, so that it does not queue
+            // ahead of them)
+            if (!ahead_done) { row_ahead(); ahead_done = true; }
             // ---- column pass: bins in order, span offsets static (as in the forward bin pass)
             const AxisTab &xt = ctl->hd[h].tab[1];
             const int NX = ctl->hd[h].nmax[1];
@@ -746,6 +774,24 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
             stg128(det_win + i, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     build_ttabs(P, ctl, tt);
+    if (P.prefetch <= -2 && P.pool_layout == RPOOL_NHWC && (P.C & 3) == 0) {
+        // row-ahead mode, head of the window: the bin rows of window rows [0, lead)
+        const int lead = -P.prefetch - 1;
+        int row = threadIdx.x;
+        for (int h = 0; h < P.n_heads; ++h) {
+            if (row >= 0 && row < P.PH[h]) {
+                const int last = (lead < y1 - y0 + 1 ? lead : y1 - y0 + 1) - 1;
+                int hi = 0;
+                for (int i = 0; i <= last; ++i) hi = tt[h].pb[i] > hi ? tt[h].pb[i] : hi;
+                if (row < hi) {
+                    const size_t row_floats = (size_t)P.PW[h] * P.C;
+                    prefetch_l2_bulk(P.pooled[h] + ((size_t)c.r * P.PH[h] + row) * row_floats,
+                                     (unsigned)(row_floats * 4));
+                }
+            }
+            row -= P.PH[h];
+        }
+    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t strip = smem_u32(smem_raw + kCtlBytes + P.n_heads * kTTabBytes) +

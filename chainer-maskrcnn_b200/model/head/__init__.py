@@ -1,1 +1,1 @@
-from .fpn_roi_pooling import FPNRoIPooling  # noqa: F401
+from .fpn_roi_pooling import FPNRoIPooling, FPNRoIKeypointPooling  # noqa: F401

@@ -139,6 +139,10 @@ RPOOL_API const char *rpool_last_error(void);
 RPOOL_API uint64_t rpool_launch_count(void);
 
 /* Tuning knobs for experiments ("prefetch", "threads", "order", "force_path").
+ * "prefetch" (backward, bulk L2 prefetch of the upstream gradient): -1 off; -1-k
+ * (k = 1..16) row-ahead, the bin rows that window row i+k is the first to need are
+ * requested while row i is processed (default -3, k = 2); n >= 0 the whole RoI of the
+ * CTA scheduled n slots later.  Results do not depend on it.
  * Unknown keys return RPOOL_ERR_INVALID. */
 RPOOL_API int rpool_set_tuning(const char *key, int value);
 RPOOL_API int rpool_get_tuning(const char *key, int *value);

@@ -127,6 +127,63 @@ def test_fused_head_call_replaces_the_per_roi_loop():
     assert torch.equal(box3, box)
 
 
+def test_keypoint_head_dispatch_including_the_single_level_shortcut():
+    # fpn_roi_keypoint_head.py:59-71: when every RoI has the same level the box
+    # features come from ONE batched call on x[0] / spatial_scales[0], whatever the
+    # level is; the mask branch (:83-87) always follows the per-RoI level
+    rng = np.random.RandomState(5)
+    n_img, C, H, W, L = 2, 32, 160, 224, 4
+    feats = synth.make_pyramid(rng, n_img, C, H, W, L)
+    from chainer_maskrcnn_b200.model.extractor.feature_pyramid_network import spatial_scales as scales
+    ft = [torch.from_numpy(f).cuda() for f in feats]
+    # person-shaped boxes that all land on one level, and not the finest
+    rois = synth.make_rois(rng, n_img, 40, H, W, size_range=(60.0, 100.0), aspect_range=(1.5, 3.0))
+    lv = oracle.levels_for_pyramid(rois[:, 1:], L)
+    assert len(np.unique(lv)) == 1 and lv[0] == 2
+    rt = torch.from_numpy(rois).cuda()
+    lvt = torch.from_numpy(lv.astype(np.float32)).cuda()
+    pooler = pkg.FPNRoIKeypointPooling(7, 14)
+    box, mask = pooler(ft, rt, lvt, scales, train=True)
+    zeros = np.zeros_like(lv)
+    assert oracle.rel_err(box.cpu().numpy(), oracle.fpn_forward(feats, rois, zeros, scales, 7)) <= 1e-5
+    assert oracle.rel_err(mask.cpu().numpy(), oracle.fpn_forward(feats, rois, lv, scales, 14)) <= 1e-5
+    # without the shortcut: box by level, like the mask head
+    box_l, mask_l = pkg.FPNRoIKeypointPooling(7, 14, reference_quirk=False)(ft, rt, lvt, scales)
+    assert oracle.rel_err(box_l.cpu().numpy(), oracle.fpn_forward(feats, rois, lv, scales, 7)) <= 1e-5
+    assert torch.equal(mask_l, mask)
+    # mixed levels: the per-RoI loop (:66-71), row r <-> RoI r
+    rois2 = synth.make_rois(rng, n_img, 40, H, W, size_range=(8.0, 300.0), aspect_range=(1.5, 3.0))
+    lv2 = oracle.levels_for_pyramid(rois2[:, 1:], L)
+    assert len(np.unique(lv2)) > 1
+    rt2 = torch.from_numpy(rois2).cuda()
+    lvt2 = torch.from_numpy(lv2.astype(np.float32)).cuda()
+    box2, mask2 = pooler(ft, rt2, lvt2, scales, train=True)
+    assert oracle.rel_err(box2.cpu().numpy(), oracle.fpn_forward(feats, rois2, lv2, scales, 7)) <= 1e-5
+    assert oracle.rel_err(mask2.cpu().numpy(), oracle.fpn_forward(feats, rois2, lv2, scales, 14)) <= 1e-5
+    # test mode + predict_mask (:93-104)
+    b3 = pooler(ft, rt, lvt, scales, train=False)
+    assert torch.equal(b3, box)
+    assert torch.equal(pooler.predict_mask(lvt, rt, scales), mask)
+
+
+@pytest.mark.parametrize("C,P,scale", [(490, 7, 1 / 16.), (1024, 7, 1 / 16.), (1024, 14, 1 / 16.)])
+def test_single_level_heads_thin_and_wide_maps(C, P, scale):
+    # light_roi_mask_head.py:26,87-92,116-117 (thin 490-channel map) and
+    # resnet_roi_mask_head.py:61-62 (1024-channel C4 map): one batched call, one map
+    rng = np.random.RandomState(C + P)
+    N, H, W = 2, 38, 50
+    x = rng.randn(N, C, H, W).astype(np.float32)
+    rois = synth.make_rois(rng, N, 24, H * 16, W * 16, size_range=(32.0, 400.0))
+    gy = synth.make_gy(rng, rois.shape[0], C, P)
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    y = _roi_align_2d_yx(xt, torch.from_numpy(rois).cuda(), P, P, scale)
+    assert tuple(y.shape) == (rois.shape[0], C, P, P)
+    rois_xy = rois[:, [0, 2, 1, 4, 3]]
+    assert oracle.rel_err(y.detach().cpu().numpy(), oracle.forward_chainer(x, rois_xy, P, P, scale, threads=8)) <= 1e-5
+    (y * torch.from_numpy(gy).cuda()).sum().backward()
+    assert oracle.rel_err(xt.grad.cpu().numpy(), oracle.backward_chainer(gy, rois_xy, x.shape, scale, threads=8)) <= 1e-4
+
+
 def test_host_fused_call_and_launch_counter():
     rng = np.random.RandomState(4)
     feats = synth.make_pyramid(rng, 1, 16, 128, 128, 4)

@@ -160,7 +160,7 @@ def test_levels_random_million_bit_exact():
 # ---------------------------------------------------------------------------
 # seeded random cases against the oracle, every kernel path
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("path,prefetch", [("auto", -1), ("generic", -1), ("table", 0), ("table", 7)])
+@pytest.mark.parametrize("path,prefetch", [("auto", -3), ("generic", -1), ("table", 0), ("table", 7), ("table", -2), ("table", -1)])
 @pytest.mark.parametrize("mode_name,S", [("chainer", 1), ("caffe2", 1), ("caffe2", 2), ("caffe2", 3)])
 def test_fused_vs_oracle(path, prefetch, mode_name, S):
     rng, feats, rois, levels, scales = make_case(seed=S * 7 + len(path))
