@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--deterministic", action="store_true",
                     help="time the deterministic (segmented reduction) backward instead of the atomic one")
     ap.add_argument("--tune", default="", help="comma list key=value for rpool_set_tuning")
+    ap.add_argument("--shard", action="store_true",
+                    help="strong scaling: ONE instance of the config, its images dealt round-robin to the "
+                         "ranks (BASELINE.json configs[3]); default is the config on every rank (weak)")
     return ap.parse_args()
 
 
@@ -298,7 +301,15 @@ def run_b200(args):
         _lib.set_tuning(**{k: int(v)})
 
     S = args.sampling_ratio
-    cfg, rng, shapes, rois_np, scales = workload(args.config, rank)
+    cfg, rng, shapes, rois_np, scales = workload(args.config, 0 if args.shard else rank)
+    if args.shard and world > 1:
+        # image n -> rank n mod world; a rank holds only its own images' pyramids, RoIs and gradients
+        if cfg["n_images"] < world:
+            raise SystemExit("--shard: %s has %d images, fewer than %d ranks" % (cfg["name"], cfg["n_images"], world))
+        rois_np, _ = _sharding.shard_rois(rois_np, cfg["n_images"], world, rank)
+        cfg["n_images"] = len(_sharding.images_of_rank(cfg["n_images"], world, rank))
+        shapes = synth.pyramid_shapes(cfg["n_images"], cfg["channels"], cfg["height"], cfg["width"],
+                                      cfg["n_levels"])
     C, R = cfg["channels"], rois_np.shape[0]
     sizes = cfg["out_sizes"]
     # features live in HBM channels-last (the layout B200 convolutions produce)
@@ -434,9 +445,11 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / K, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong" if args.shard else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
         "config": {
-            "workload": cfg["name"] + " per GPU", "baseline_config_index": args.config,
+            "workload": cfg["name"] + (" sharded by image over %d GPUs" % world if args.shard else " per GPU"),
+            "baseline_config_index": args.config,
             "rois_per_gpu": R, "channels": C, "out_sizes": sizes, "sampling_ratio": S,
             "levels": "P2-P%d, assigned on device by the reference rule" % (cfg["n_levels"] + 1),
             "layout": "channels-last features/pooled/gradients resident in HBM",

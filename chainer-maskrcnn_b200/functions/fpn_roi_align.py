@@ -33,6 +33,10 @@ def fpn_roi_align(x, indices_and_rois, levels, spatial_scales, out_sizes,
     Differentiable with respect to every level of ``x``."""
     single = not isinstance(out_sizes, list)
     sizes = [out_sizes] if single else out_sizes
+    # the reference indexes spatial_scales[l] per RoI: a list longer than the pyramid is fine
+    if len(spatial_scales) < len(x):
+        raise ValueError("one spatial_scale per level: %d scales for %d levels" % (len(spatial_scales), len(x)))
+    spatial_scales = list(spatial_scales)[:len(x)]
     cfg = dict(spatial_scales=list(spatial_scales), out_sizes=sizes,
                sampling_ratio=sampling_ratio, roi_format=_lib.ROI_YX)
     if coord_mode is not None:
