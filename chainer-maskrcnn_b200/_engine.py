@@ -51,7 +51,15 @@ def level_thresholds(k_min=0, k_max=4, s0=224, lvl0=4, eps=1e-6):
 # ---------------------------------------------------------------------------
 # helpers
 # ---------------------------------------------------------------------------
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """Handle of torch's current stream on the current device.  The raw accessor is
+    used when torch has it: torch.cuda.current_stream() builds a Stream object through
+    several Python layers (14 us per call here; three calls per forward + backward)."""
+    if _RAW_STREAM is not None:
+        return ctypes.c_void_p(_RAW_STREAM(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -92,11 +100,44 @@ class Plan(object):
     """Everything backward needs: geometry, RoIs, the device schedule."""
     __slots__ = ("shapes", "scales", "rois", "levels_i32", "levels_f32", "thresholds", "k_min",
                  "out_sizes", "sampling_ratio", "coord_mode", "roi_format", "workspace",
-                 "channels", "device")
+                 "channels", "device", "problem")
+
+
+class _NoGuard(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on(device):
+    """Device guard for the launches: nothing when `device` is already current (the
+    usual case; the torch guard costs several microseconds per call)."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
 
 
 def _fill_problem(plan, level_ptrs, pooled_ptrs, accumulate=False, deterministic=False):
-    p = _lib.Problem()
+    """The plan's rpool_problem block with this call's addresses patched in.  The
+    geometry is written once per plan; ctypes field stores are the bulk of the host
+    time of a small call."""
+    p = plan.problem
+    if p is not None:
+        for l, ptr in enumerate(level_ptrs):
+            p.level[l].data = ptr
+        for h, ptr in enumerate(pooled_ptrs):
+            p.pooled[h] = ptr
+        p.accumulate = int(accumulate)
+        p.deterministic = int(deterministic)
+        p.det_workspace = None
+        p.det_workspace_bytes = 0
+        return p
+    p = plan.problem = _lib.Problem()
     p.n_levels = len(plan.shapes)
     p.channels = plan.channels
     p.feat_layout = _lib.NHWC
@@ -166,6 +207,7 @@ def make_plan(shapes, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
         coord_mode = default_coord_mode(sampling_ratio)
 
     plan = Plan()
+    plan.problem = None
     plan.device = rois.device
     plan.shapes = shapes
     plan.scales = [float(s) for s in spatial_scales]
@@ -198,7 +240,7 @@ def make_plan(shapes, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
     # rpool_plan reads geometry only; level/pooled addresses are not dereferenced
     dummy = plan.workspace.data_ptr()
     prob = _fill_problem(plan, [dummy] * len(shapes), [None] * len(plan.out_sizes))
-    with torch.cuda.device(rois.device):
+    with _on(rois.device):
         _lib.check(L.rpool_plan(ctypes.byref(prob), plan.workspace.data_ptr(), ws_bytes, _stream()))
     return plan
 
@@ -222,7 +264,7 @@ def forward(features, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
     outs = [torch.empty((R, C, oh, ow), dtype=torch.float32, device=plan.device,
                         memory_format=torch.channels_last) for oh, ow in plan.out_sizes]
     prob = _fill_problem(plan, [f.data_ptr() for f in feats], [o.data_ptr() for o in outs])
-    with torch.cuda.device(plan.device):
+    with _on(plan.device):
         _lib.check(_lib.lib().rpool_forward(ctypes.byref(prob), plan.workspace.data_ptr(),
                                             plan.workspace.numel(), _stream()))
     return outs, plan
@@ -256,7 +298,7 @@ def backward(plan, gys, deterministic=False, out=None):
     prob = _fill_problem(plan, [g.data_ptr() for g in grads], [g.data_ptr() for g in g_in],
                          accumulate=False, deterministic=deterministic)
     L = _lib.lib()
-    with torch.cuda.device(plan.device):
+    with _on(plan.device):
         ws, ws_n = plan.workspace.data_ptr(), plan.workspace.numel()
         if deterministic:
             # the scratch holds one private window per RoI: its size depends on the

@@ -197,13 +197,25 @@ int fill_params(const rpool_problem *p, const Workspace &w, bool bwd, int thread
     return ctl + p->n_heads * ttab + warps * k.strip_cols * 512;
 }
 
+// Raises a pooling kernel's dynamic shared memory limit.  The limit is per device
+// and only ever needs to grow, so the largest value set so far is remembered per
+// (kernel, device) and the driver call is skipped when it already covers `smem`.
+constexpr int kSmemCacheDevices = 64;
+std::atomic<int> g_smem_set[2][kSmemCacheDevices];
+
 template <typename Kern>
-int set_smem(Kern kern, int smem)
+int set_smem(Kern kern, int which, int smem)
 {
-    // Raising the dynamic shared memory limit is per device and cheap; do it
-    // on every launch so that multi-device processes need no bookkeeping.
+    int dev = -1;
+    CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+    const bool cached = dev >= 0 && dev < kSmemCacheDevices;
+    if (cached && g_smem_set[which][dev].load(std::memory_order_relaxed) >= smem) return RPOOL_OK;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
              "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    if (cached) {
+        int seen = g_smem_set[which][dev].load(std::memory_order_relaxed);
+        while (seen < smem && !g_smem_set[which][dev].compare_exchange_weak(seen, smem)) {}
+    }
     return RPOOL_OK;
 }
 
@@ -363,7 +375,7 @@ int rpool_forward(const rpool_problem *p, void *ws, size_t ws_size, void *stream
     if (smem > kMaxSmem)
         return fail(RPOOL_ERR_UNSUPPORTED, "forward needs %d bytes of shared memory; the limit is %d",
                     smem, kMaxSmem);
-    rc = set_smem(rpool_forward_kernel, smem);
+    rc = set_smem(rpool_forward_kernel, 0, smem);
     if (rc) return rc;
     rpool_forward_kernel<<<p->n_rois, threads, smem, static_cast<cudaStream_t>(stream)>>>(k);
     CUDA_TRY(cudaGetLastError(), "rpool_forward_kernel launch");
@@ -457,7 +469,7 @@ static int backward_det(const rpool_problem *p, void *ws, cudaStream_t st)
         k.det = 1;
         k.det_scratch = static_cast<float *>(p->det_workspace);
         k.det_scratch_floats = p->det_workspace_bytes / sizeof(float);
-        rc = set_smem(rpool_backward_kernel, smem);
+        rc = set_smem(rpool_backward_kernel, 1, smem);
         if (rc) return rc;
         rpool_backward_kernel<<<p->n_rois, threads, smem, st>>>(k);
         CUDA_TRY(cudaGetLastError(), "rpool_backward_kernel launch");
@@ -525,7 +537,7 @@ int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *strea
         threads -= 32;
         smem = fill_params(p, ws_split(ws, p), true, threads, k);
     }
-    rc = set_smem(rpool_backward_kernel, smem);
+    rc = set_smem(rpool_backward_kernel, 1, smem);
     if (rc) return rc;
     rpool_backward_kernel<<<p->n_rois, threads, smem, st>>>(k);
     CUDA_TRY(cudaGetLastError(), "rpool_backward_kernel launch");
