@@ -87,6 +87,25 @@ def ncu_traffic(cfg_id, S, kernels):
         return None
 
 
+def ncu_view(cfg_id, S):
+    """What the committed ncu capture says about the pooling kernels of this workload:
+    DRAM GB/s (dram bytes / gpu__time_duration) and L2 hit rate per kernel, against the
+    nominal 8 TB/s of the part (north_star) -- None when the workload was not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)["cfg%d_S%d" % (cfg_id, S)]
+        out = {"source": "profiles/ncu_traffic.json (ncu --set full --clock-control none, one launch each)"}
+        for name, v in t.items():
+            if "us" not in v:
+                continue
+            gbs = (v["read"] + v["write"]) / (v["us"] * 1e-6) / 1e9
+            out[name] = {"dram_GBps": gbs, "frac_of_8TBps": gbs / 8000.0, "l2_hit_pct": v.get("l2_hit_pct"),
+                         "us": v["us"]}
+        return out
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -415,6 +434,7 @@ def run_b200(args):
         "traffic_source": "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, "
                           "ncu --set full, per launch)",
         "peak_source": peak_src,
+        "ncu": ncu_view(args.config, S),
         "kernel": ("rpool_zero_kernel + rpool_backward_kernel" if dom == "backward"
                    else "rpool_plan_kernel + rpool_forward_kernel"),
         "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms,
