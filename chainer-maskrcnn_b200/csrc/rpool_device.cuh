@@ -352,10 +352,6 @@ __device__ __forceinline__ void red_add_f32(float *p, float v)
     asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
 }
 
-__device__ __forceinline__ void prefetch_l1(const float *p)
-{
-    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
-}
 // bulk L2 prefetch through the TMA unit (bytes: multiple of 16)
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 {

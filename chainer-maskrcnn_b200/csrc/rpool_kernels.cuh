@@ -652,16 +652,6 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
                 const bool two = pa + 1 < pb;
                 load_bins(Z, g);
                 load_bins(v, g + (two ? gstep : 0));
-#ifdef RPOOL_L1PF
-                if (kExact) {
-                    // experiment: ask L1 for what this task loads next (the third covering row
-                    // of this half, the first rows of the next half)
-#if RPOOL_L1PF & 1
-                    if (pa + 2 < pb) {
-#pragma unroll
-                        for (int k = 0; k < kZ; ++k) prefetch_l1(g + 2 * (size_t)gstep + k * kC);
-                    }
-#endif
 #if RPOOL_L1PF & 2
                     if (pw0 + kZ < PW) {
 #pragma unroll
