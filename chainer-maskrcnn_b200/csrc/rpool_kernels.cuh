@@ -652,18 +652,6 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
                 const bool two = pa + 1 < pb;
                 load_bins(Z, g);
                 load_bins(v, g + (two ? gstep : 0));
-#if RPOOL_L1PF & 2
-                    if (pw0 + kZ < PW) {
-#pragma unroll
-                        for (int k = 0; k < kZ; ++k) prefetch_l1(g + (kZ + k) * kC);
-                        if (two) {
-#pragma unroll
-                            for (int k = 0; k < kZ; ++k) prefetch_l1(g + gstep + (kZ + k) * kC);
-                        }
-                    }
-#endif
-                }
-#endif
                 {
                     const float w0 = wrow[pa], w1 = two ? wrow[pa + 1] : 0.f;
 #pragma unroll
