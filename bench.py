@@ -35,12 +35,12 @@ UNIT = "RoIs/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=1, help="index into BASELINE.json configs (0..3)")
     ap.add_argument("--sampling-ratio", type=int, default=2)
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
@@ -116,17 +116,45 @@ def measured_peak():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region.
+
+    NVML is polled from a thread every 2 ms (the timed region of the default run is
+    tens of milliseconds: `nvidia-smi -lms` cannot sample faster than 100 ms); the
+    `nvidia-smi` loop is the fallback when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows = []
+        self.rows = []          # nvidia-smi fallback
+        self.sm, self.reasons, self.power = [], set(), []
+        self.sm_max = None
         self.proc = None
         self.gpu = gpu_index
+        self.nvml = None
+        self.stop_flag = threading.Event()
+        self.t = None
+
+    def _nvml_index(self):
+        # CUDA_VISIBLE_DEVICES remaps torch's device order; NVML enumerates the physical parts
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        if ids and self.gpu < len(ids) and ids[self.gpu].isdigit():
+            return int(ids[self.gpu])
+        return self.gpu
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
@@ -137,11 +165,47 @@ class ClockSampler(object):
         except Exception:  # noqa: BLE001
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        names = [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"),
+                 ("hw_power_brake_slowdown", "nvmlClocksEventReasonHwPowerBrakeSlowdown")]
+        bits = [(n, getattr(nv, a)) for n, a in names if hasattr(nv, a)]
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                if get_reasons is not None:
+                    r = int(get_reasons(self.handle))
+                    for n, b in bits:
+                        if r & b:
+                            self.reasons.add(n)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=2)
+            out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                   "sm_min_mhz": float(min(self.sm)) if self.sm else None,
+                   "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                   "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None,
+                   "how": "NVML polled every 2 ms inside the timed region"}
+            try:
+                self.nvml.nvmlShutdown()
+            except Exception:  # noqa: BLE001
+                pass
+            return out
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -163,7 +227,7 @@ class ClockSampler(object):
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "how": "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------------------
