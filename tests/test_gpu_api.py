@@ -184,6 +184,48 @@ def test_single_level_heads_thin_and_wide_maps(C, P, scale):
     assert oracle.rel_err(xt.grad.cpu().numpy(), oracle.backward_chainer(gy, rois_xy, x.shape, scale, threads=8)) <= 1e-4
 
 
+def test_step_is_cuda_graph_capturable_and_replays_on_new_rois():
+    # plan + forward + zero fill + backward have no host synchronisation and no host-side
+    # data-dependent sizes: capture once, replay after the RoIs changed in place
+    rng = np.random.RandomState(11)
+    n_img, C, H, W, L = 2, 32, 160, 224, 4
+    feats = synth.make_pyramid(rng, n_img, C, H, W, L)
+    scales = [1.0 / s for s in synth.STRIDES[:L]]
+    rois_a = synth.make_rois(rng, n_img, 60, H, W, size_range=(8.0, 300.0))
+    rois_b = synth.make_rois(rng, n_img, 60, H, W, size_range=(8.0, 300.0))
+    gy = synth.make_gy(rng, rois_a.shape[0], C, 7)
+    from chainer_maskrcnn_b200 import _engine
+    ft = [torch.from_numpy(f).cuda().contiguous(memory_format=torch.channels_last) for f in feats]
+    rois = torch.from_numpy(rois_a).cuda()
+    gyt = torch.from_numpy(gy).cuda().contiguous(memory_format=torch.channels_last)
+    grads = [torch.empty_like(f) for f in ft]
+
+    def step():
+        outs, plan = _engine.forward(ft, rois, None, scales, [7], sampling_ratio=2)
+        _engine.backward(plan, [gyt], out=grads)
+        return outs[0]
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = step()
+    for r in (rois_b, rois_a, rois_b):
+        rois.copy_(torch.from_numpy(r).cuda())
+        g.replay()
+        torch.cuda.synchronize()
+        lv = oracle.levels_for_pyramid(r[:, 1:], L)
+        want = oracle.fpn_forward(feats, r, lv, scales, 7, "caffe2", 2)
+        assert oracle.rel_err(out.cpu().numpy(), want) <= 1e-5
+        want_g = oracle.fpn_backward(gy, [f.shape for f in feats], r, lv, scales, "caffe2", 2)
+        for l in range(L):
+            assert oracle.rel_err(grads[l].cpu().numpy(), want_g[l]) <= 1e-4
+
+
 def test_host_fused_call_and_launch_counter():
     rng = np.random.RandomState(4)
     feats = synth.make_pyramid(rng, 1, 16, 128, 128, 4)
