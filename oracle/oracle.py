@@ -240,12 +240,12 @@ def fpn_forward(features, indices_and_rois, levels, spatial_scales, out_size,
     levels = np.asarray(levels).astype(np.int32)
     R = rois_xy.shape[0]
     C = features[0].shape[1]
-    out = np.zeros((R, C, out_size, out_size), np.float32)
+    oh, ow = out_size if isinstance(out_size, (tuple, list)) else (out_size, out_size)
+    out = np.zeros((R, C, oh, ow), np.float32)
     for l in range(len(features)):
         sel = np.nonzero(levels == l)[0]
         if sel.size:
-            out[sel] = fwd(features[l], rois_xy[sel], out_size, out_size,
-                           spatial_scales[l], threads)
+            out[sel] = fwd(features[l], rois_xy[sel], oh, ow, spatial_scales[l], threads)
     return out
 
 
