@@ -1,4 +1,4 @@
-"""ctypes front-end of oracle/refgpu_baseline.cu.  TEST/BENCH INFRASTRUCTURE ONLY.
+"""ctypes front-end of baseline/refgpu_baseline.cu.  TEST/BENCH INFRASTRUCTURE ONLY.
 
 The reference's CuPy kernels (roi_align_2d.py:100-144, :196-279) restated in
 CUDA and driven per RoI like the reference's FPN heads

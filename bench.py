@@ -291,20 +291,22 @@ def cpu_arm(cfg_id, S, sample_rois, repeats=1):
 
 def gpu_baseline_arm(cfg_id, sample_rois, device, repeats=3):
     """Same-box GPU baseline: the reference's CuPy kernels restated in CUDA
-    (oracle/refgpu_baseline.cu) and dispatched per RoI like the reference's FPN
+    (baseline/refgpu_baseline.cu) and dispatched per RoI like the reference's FPN
     heads, on a bounded sample of the workload (its cost grows with the level
     map, not with the RoI: every backward call touches a whole dense gradient)."""
     import torch
-    from oracle import refgpu
-    import oracle
+    from baseline import refgpu
+    from chainer_maskrcnn_b200 import _engine
     cfg, rng, shapes, rois, scales = workload(cfg_id, 0)
     sample_rois = min(sample_rois, rois.shape[0])
     sel = np.sort(np.random.RandomState(99).choice(rois.shape[0], sample_rois, replace=False))
     sub = rois[sel]
-    levels = oracle.levels_for_pyramid(sub[:, 1:], cfg["n_levels"])
+    # levels by the product's own device mapper (bit-exact image of the reference rule)
+    levels = _engine.assign_levels(torch.from_numpy(sub).to(device), as_int=True,
+                                   k_cap=cfg["n_levels"] - 1).cpu().numpy()
     feats = [torch.randn(s, device=device, dtype=torch.float32) for s in shapes]
     state = refgpu.FpnState(feats, scales)
-    rois_xy = torch.from_numpy(oracle.roi_yx_to_xy(sub)).to(device)
+    rois_xy = torch.from_numpy(np.ascontiguousarray(sub[:, [0, 2, 1, 4, 3]])).to(device)
     total_ms, ops = 0.0, 0
     for P in cfg["out_sizes"]:
         top = torch.empty((sample_rois, cfg["channels"], P, P), device=device)
@@ -323,7 +325,7 @@ def gpu_baseline_arm(cfg_id, sample_rois, device, repeats=3):
         total_ms += best
         ops += n_ops
     return {"value": sample_rois / (total_ms * 1e-3), "unit": UNIT, "kind": "reference CuPy kernels restated "
-            "(oracle/refgpu_baseline.cu), per-RoI dispatch of fpn_roi_mask_head.py:57-63, sampling_ratio 1, "
+            "(baseline/refgpu_baseline.cu), per-RoI dispatch of fpn_roi_mask_head.py:57-63, sampling_ratio 1, "
             "NCHW", "sample": "%d of %d RoIs of %s (seed 99)" % (sample_rois, rois.shape[0], cfg["name"]),
             "ms": total_ms, "device_ops": ops}
 

@@ -257,12 +257,12 @@ def test_errors_are_loud():
 
 @pytest.mark.gpu
 def test_restated_cupy_kernels_agree_with_the_numpy_reference():
-    """The same-box GPU baseline (oracle/refgpu_baseline.cu restates the reference's
+    """The same-box GPU baseline (baseline/refgpu_baseline.cu restates the reference's
     CuPy kernels, roi_align_2d.py:100-144 / :196-279) must compute the reference's
     op: forward within 1e-5 of the NumPy-path oracle; backward within 1e-4 on RoIs
     whose taps never coincide (the CuPy backward drops coincident-cell taps,
     :256-272, the NumPy backward does not)."""
-    from oracle import refgpu
+    from baseline import refgpu
     rng = np.random.RandomState(5)
     x = rng.standard_normal((2, 8, 40, 56)).astype(np.float32)
     rois_yx = synth.make_rois(rng, 2, 24, 160, 224, size_range=(40.0, 150.0))
