@@ -107,6 +107,22 @@ def ncu_view(cfg_id, S):
         return None
 
 
+def reference_numpy_numbers(cfg_name):
+    """The reference's own NumPy path cannot travel to the GPU box; what it does on this
+    workload was measured in the development container by tools/reference_numpy_timing.py
+    and is quoted from the committed result."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_reference_numpy_cpu.json")) as f:
+            d = json.load(f)
+        c = d["configs"][cfg_name]
+        return {"rois_per_s_1core": c["one_core"]["rois_per_s"],
+                "rois_per_s_all_cores": c["all_cores"]["rois_per_s"], "cores": c["all_cores"]["processes"],
+                "sample_rois": c["sample_rois"], "where": d["where"],
+                "source": "profiles/r01_reference_numpy_cpu.json (tools/reference_numpy_timing.py)"}
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -286,6 +302,7 @@ def cpu_arm(cfg_id, S, sample_rois, repeats=1):
             if m.size:
                 oracle.ref_caffe2_forward(feats[l], rois_xy[m], P, P, scales[l], max(S, 1))
         info["reference_cpp_forward_rois_per_s_1thread"] = n / (time.perf_counter() - t0)
+    info["reference_numpy_path"] = reference_numpy_numbers(cfg["name"])
     return info["value"], info
 
 
