@@ -270,10 +270,13 @@ def forward(features, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
     return outs, plan
 
 
-def backward(plan, gys, deterministic=False, out=None):
+def backward(plan, gys, deterministic=False, out=None, accumulate=False):
     """Dense feature gradients (channels-last memory, logical (N,C,H,W)) for
     every level from the pooled gradients ``gys`` (one per head).  ``out``: optional
-    preallocated gradient tensors to write into."""
+    preallocated gradient tensors to write into; with ``accumulate=True`` the result
+    is added to what ``out`` already holds (no zero fill: rpool_problem.accumulate)."""
+    if accumulate and out is None:
+        raise ValueError("accumulate=True needs the gradient tensors to add into (out=...)")
     if len(gys) != len(plan.out_sizes):
         raise ValueError("one gy per head")
     R = plan.rois.shape[0]
@@ -296,7 +299,7 @@ def backward(plan, gys, deterministic=False, out=None):
             if tuple(g.shape) != shape or not g.is_contiguous(memory_format=torch.channels_last):
                 raise ValueError("out gradients must be channels-last tensors of the feature shapes")
     prob = _fill_problem(plan, [g.data_ptr() for g in grads], [g.data_ptr() for g in g_in],
-                         accumulate=False, deterministic=deterministic)
+                         accumulate=accumulate, deterministic=deterministic)
     L = _lib.lib()
     with _on(plan.device):
         ws, ws_n = plan.workspace.data_ptr(), plan.workspace.numel()

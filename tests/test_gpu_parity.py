@@ -382,6 +382,27 @@ def test_deterministic_backward_edge_cases():
         _engine.backward(plan, [dev(synth.make_gy(rng, rois.shape[0], 8, 20))], deterministic=True)
 
 
+@pytest.mark.parametrize("deterministic", [False, True])
+def test_backward_accumulates_into_existing_gradients(deterministic):
+    # rpool_problem.accumulate: the box and the mask head pooled by two separate calls add
+    # into the same dense gradients (what Chainer's autograd does with the per-call results)
+    rng, feats, rois, levels, scales = make_case(seed=21, C=32, per_img=80)
+    gy7 = synth.make_gy(rng, rois.shape[0], 32, 7)
+    gy14 = synth.make_gy(rng, rois.shape[0], 32, 14)
+    f = [dev(x, True) for x in feats]
+    _, plan7 = _engine.forward(f, dev(rois), None, scales, [7], sampling_ratio=2)
+    _, plan14 = _engine.forward(f, dev(rois), None, scales, [14], sampling_ratio=2)
+    grads = [torch.full_like(x, float("nan")) for x in f]          # the first call must overwrite
+    _engine.backward(plan7, [dev(gy7, True)], out=grads, deterministic=deterministic)
+    _engine.backward(plan14, [dev(gy14, True)], out=grads, accumulate=True, deterministic=deterministic)
+    torch.cuda.synchronize()
+    _, want = oracle_fused(feats, rois, levels, scales, [7, 14], 2, "caffe2", [gy7, gy14])
+    for g, w in zip(grads, want):
+        assert oracle.rel_err(host(g), w) <= BWD_TOL
+    with pytest.raises(ValueError):
+        _engine.backward(plan7, [dev(gy7, True)], accumulate=True)
+
+
 def test_layout_conversion_kernels():
     rng = np.random.RandomState(15)
     x = rng.standard_normal((3, 37, 19, 45)).astype(np.float32)
