@@ -594,7 +594,7 @@ def run_b200(args):
             "l2": "no flush: one step touches %.0f MB >> 126 MB L2"
                   % ((ab["O"] * 2 + ab["F"] * 2) / 1e6),
             "sharding": "by image, one process per GPU, no data-path collective",
-            "tuning": {k: _lib.get_tuning(k) for k in ("prefetch", "threads", "order", "force_path")},
+            "tuning": {k: _lib.get_tuning(k) for k in ("prefetch", "threads", "order", "force_path", "split_heads")},
         },
         "fwd_ms": fwd_ms_max, "bwd_ms": bwd_ms_max,
         "roofline": roofline, "cpu_baseline": cpu, "gpu_baseline": gpu_base, "e2e": e2e,

@@ -24,6 +24,7 @@ std::atomic<int> g_prefetch{-3};
 std::atomic<int> g_threads{128};
 std::atomic<int> g_order{1};
 std::atomic<int> g_force_path{kPathAuto};
+std::atomic<int> g_split_heads{1};
 
 int fail(int code, const char *fmt, ...)
 {
@@ -247,6 +248,9 @@ int rpool_set_tuning(const char *key, int value)
     } else if (!strcmp(key, "force_path")) {
         if (value < 0 || value > 2) return fail(RPOOL_ERR_INVALID, "force_path=%d outside [0,2]", value);
         g_force_path = value;
+    } else if (!strcmp(key, "split_heads")) {
+        if (value < 0 || value > 1) return fail(RPOOL_ERR_INVALID, "split_heads=%d outside [0,1]", value);
+        g_split_heads = value;
     } else {
         return fail(RPOOL_ERR_INVALID, "unknown tuning key '%s'", key);
     }
@@ -260,6 +264,7 @@ int rpool_get_tuning(const char *key, int *value)
     else if (!strcmp(key, "threads")) *value = g_threads;
     else if (!strcmp(key, "order")) *value = g_order;
     else if (!strcmp(key, "force_path")) *value = g_force_path;
+    else if (!strcmp(key, "split_heads")) *value = g_split_heads;
     else return fail(RPOOL_ERR_INVALID, "unknown tuning key '%s'", key);
     return RPOOL_OK;
 }
@@ -530,18 +535,34 @@ int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *strea
         g_launches++;
     }
     if (p->n_rois == 0) return RPOOL_OK;
-    KParams k;
-    int threads = g_threads.load();
-    int smem = fill_params(p, ws_split(ws, p), true, threads, k);
-    while (smem > kMaxSmem && threads > 32) {  // two wide heads: fewer warps, same result
-        threads -= 32;
-        smem = fill_params(p, ws_split(ws, p), true, threads, k);
+    const Workspace w = ws_split(ws, p);
+    // Two pooled sizes: the backward pass has nothing to share between them (each reads its
+    // own gy; the reductions into the gradient are per size either way), and one launch per
+    // size keeps the per-CTA strips small (more L1 for the gy re-reads): 2 launches unless
+    // "split_heads" is 0.
+    const int parts = (p->n_heads > 1 && g_split_heads.load()) ? p->n_heads : 1;
+    for (int part = 0; part < parts; ++part) {
+        rpool_problem q = *p;
+        if (parts > 1) {
+            q.n_heads = 1;
+            q.out_h[0] = p->out_h[part];
+            q.out_w[0] = p->out_w[part];
+            q.pooled[0] = p->pooled[part];
+        }
+        KParams k;
+        int threads = g_threads.load();
+        int smem = fill_params(&q, w, true, threads, k);
+        while (smem > kMaxSmem && threads > 32) {  // two wide heads: fewer warps, same result
+            threads -= 32;
+            smem = fill_params(&q, w, true, threads, k);
+        }
+        k.rec_head = parts > 1 ? part : 0;
+        rc = set_smem(rpool_backward_kernel, 1, smem);
+        if (rc) return rc;
+        rpool_backward_kernel<<<p->n_rois, threads, smem, st>>>(k);
+        CUDA_TRY(cudaGetLastError(), "rpool_backward_kernel launch");
+        g_launches++;
     }
-    rc = set_smem(rpool_backward_kernel, 1, smem);
-    if (rc) return rc;
-    rpool_backward_kernel<<<p->n_rois, threads, smem, st>>>(k);
-    CUDA_TRY(cudaGetLastError(), "rpool_backward_kernel launch");
-    g_launches++;
     return RPOOL_OK;
 }
 

@@ -63,6 +63,7 @@ struct KParams {
                      // (default k = 2); >= 0 whole RoI of the CTA scheduled that many slots later
     const unsigned char *recs;  // per-slot RoI records (rpool_tables_kernel), rec_stride bytes apart
     int rec_stride;
+    int rec_head;    // first head part of the stored record this launch uses (0 unless heads are split)
     int force_path;
 };
 

@@ -75,8 +75,13 @@ __device__ __forceinline__ void load_record(const KParams &P, BlockCtl *ctl)
 {
     const uint4 *src = reinterpret_cast<const uint4 *>(P.recs + (size_t)launch_slot(P) * P.rec_stride);
     uint4 *dst = reinterpret_cast<uint4 *>(ctl);
+    // header, then this launch's n_heads head parts starting at part rec_head of the stored
+    // record (a launch over one pooled size of a two-size plan reads its own part as head 0)
+    constexpr int kHdr16 = kRecHeader >> 4;
+    const int skip16 = P.rec_head * (int)(sizeof(HeadCtl) >> 4);
     const int n16 = rec_bytes(P.n_heads) >> 4;
-    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x)
+        dst[i] = __ldg(src + (i < kHdr16 ? i : i + skip16));
     __syncthreads();
 }
 

@@ -138,7 +138,9 @@ RPOOL_API const char *rpool_last_error(void);
 /* Number of kernels this library has launched in the calling process. */
 RPOOL_API uint64_t rpool_launch_count(void);
 
-/* Tuning knobs for experiments ("prefetch", "threads", "order", "force_path").
+/* Tuning knobs for experiments ("prefetch", "threads", "order", "force_path", "split_heads").
+ * "split_heads": 1 (default) runs the backward pass of a two-size problem as one launch
+ * per pooled size (the sizes share nothing in that direction); 0 = one launch for both.
  * "prefetch" (backward, bulk L2 prefetch of the upstream gradient): -1 off; -1-k
  * (k = 1..16) row-ahead, the bin rows that window row i+k is the first to need are
  * requested while row i is processed (default -3, k = 2); n >= 0 the whole RoI of the

@@ -27,7 +27,7 @@ PATHS = {"auto": _lib.PATH_AUTO, "generic": _lib.PATH_GENERIC, "table": _lib.PAT
 
 @pytest.fixture(autouse=True)
 def _reset_tuning():
-    defaults = {k: _lib.get_tuning(k) for k in ("prefetch", "threads", "order", "force_path")}
+    defaults = {k: _lib.get_tuning(k) for k in ("prefetch", "threads", "order", "force_path", "split_heads")}
     yield
     _lib.set_tuning(**defaults)
 
@@ -188,6 +188,27 @@ def test_block_sizes(threads):
     assert oracle.rel_err(outs[0], want[0]) <= FWD_TOL
     for g, w in zip(grads, wgrads):
         assert oracle.rel_err(g, w) <= BWD_TOL
+
+
+@pytest.mark.parametrize("split", [0, 1])
+@pytest.mark.parametrize("mode_name,S", [("chainer", 1), ("caffe2", 2)])
+def test_two_pooled_sizes_backward_fused_or_one_launch_per_size(split, mode_name, S):
+    # "split_heads": one backward launch per pooled size (default) or one for both
+    _lib.set_tuning(split_heads=split)
+    rng, feats, rois, levels, scales = make_case(31, per_img=120)
+    C = feats[0].shape[1]
+    gys = [synth.make_gy(rng, rois.shape[0], C, 7), synth.make_gy(rng, rois.shape[0], C, 14)]
+    outs, grads, plan = run_fused(feats, rois, None, scales, [7, 14], S=S, gys=gys)
+    g_cl = [dev(g, True) for g in gys]
+    n0 = _lib.launch_count()
+    _engine.backward(plan, g_cl)
+    launches = _lib.launch_count() - n0
+    want, want_g = oracle_fused(feats, rois, levels, scales, [7, 14], S, mode_name, gys)
+    for o, w in zip(outs, want):
+        assert oracle.rel_err(o, w) <= FWD_TOL
+    for g, w in zip(grads, want_g):
+        assert oracle.rel_err(g, w) <= BWD_TOL
+    assert launches == 1 + (2 if split else 1)   # zero fill + backward launch(es)
 
 
 def test_rectangular_output_and_odd_channels():
