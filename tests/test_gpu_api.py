@@ -242,6 +242,40 @@ def test_host_fused_call_and_launch_counter():
         assert g.shape == w.shape and oracle.rel_err(g, w) <= 1e-4
 
 
+@pytest.mark.parametrize("order", ["image_major", "interleaved"])
+def test_host_call_pipelined_over_image_groups(order):
+    # image-major RoIs: the host call is pipelined over groups of images; any other order
+    # takes the single-group path.  Same results either way, rows in input order.
+    rng = np.random.RandomState(6)
+    n_img, C, H, W, L = 5, 16, 128, 160, 3
+    feats = synth.make_pyramid(rng, n_img, C, H, W, L)
+    rois = synth.make_rois(rng, n_img, 30, H, W, size_range=(8.0, 150.0))
+    rois = rois[rois[:, 0] != 3]                      # an image without RoIs
+    if order == "interleaved":
+        rng.shuffle(rois)
+    from chainer_maskrcnn_b200.functions.fpn_roi_align import _image_groups
+    assert len(_image_groups(rois, n_img)) == (4 if order == "image_major" else 1)
+    scales = [1.0 / s for s in synth.STRIDES[:L]]
+    lv = oracle.levels_for_pyramid(rois[:, 1:], L)
+    gys = [synth.make_gy(rng, rois.shape[0], C, 7), synth.make_gy(rng, rois.shape[0], C, 14)]
+    for levels in (None, lv.astype(np.float32)):
+        pooled, grads = pkg.fpn_roi_align_host(feats, rois, levels, scales, [7, 14], 2, gys=gys)
+        want_g = [np.zeros_like(f) for f in feats]
+        for P, o, gy in zip((7, 14), pooled, gys):
+            assert o.shape == (rois.shape[0], C, P, P)
+            assert oracle.rel_err(o, oracle.fpn_forward(feats, rois, lv, scales, P, "caffe2", 2)) <= 1e-5
+            for l, part in enumerate(oracle.fpn_backward(gy, [f.shape for f in feats], rois, lv, scales,
+                                                         "caffe2", 2)):
+                want_g[l] += part
+        for g, w in zip(grads, want_g):
+            assert g.shape == w.shape and oracle.rel_err(g, w) <= 1e-4
+            assert np.all(g[3] == 0)
+    # forward only
+    pooled, grads = pkg.fpn_roi_align_host(feats, rois, None, scales, 7, 1)
+    assert grads is None
+    assert oracle.rel_err(pooled[0], oracle.fpn_forward(feats, rois, lv, scales, 7)) <= 1e-5
+
+
 def test_errors_are_loud():
     x = torch.zeros(1, 4, 8, 8).cuda()
     r = torch.zeros(2, 5).cuda()
