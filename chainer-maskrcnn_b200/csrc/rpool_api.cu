@@ -182,7 +182,7 @@ int fill_params(const rpool_problem *p, const Workspace &w, bool bwd, int thread
     k.S = p->sampling_ratio;
     k.mode = p->coord_mode;
     k.force_path = g_force_path.load();
-    const int ctl = (int)((sizeof(BlockCtl) + 127) & ~(size_t)127);
+    const int ctl = (rec_bytes(p->n_heads) + 127) & ~127;
     const int warps = threads / 32;
     k.prefetch = g_prefetch.load();
     k.reverse = (bwd && g_order.load() == 1) ? 1 : 0;

@@ -513,20 +513,25 @@ rpool_forward_kernel(const __grid_constant__ KParams P)
 // are pulled into L2 with one bulk prefetch (TMA unit) per bin row while the column
 // pass of the current task runs.
 struct TTab {
-    float w[kExt][kPBwd];
-    int pa[kExt], pb[kExt];  // covering bins of row/column i: [pa, pb)
+    int pa[kExt], pb[kExt];  // covering bin rows of window row i: [pa, pb)
 };
+
+// Weight of bin row ph on window row y (absolute): component y - lo[ph] of the forward
+// footprint entry, read straight from the record (0 outside the footprint).
+__device__ __forceinline__ float wy_of(const AxisTab &yt, int ph, int y)
+{
+    const int k = y - yt.lo[ph];
+    return (k >= 0 && k < yt.n[ph]) ? reinterpret_cast<const float *>(&yt.w[ph])[k] : 0.f;
+}
 
 __device__ __forceinline__ void build_ttabs(const KParams &P, const BlockCtl *ctl, TTab *tt)
 {
-    // one transposed table per head, for the y axis: window row -> covering bin rows
+    // per head, for the y axis: window row -> the contiguous run of bin rows covering it
+    // (footprints start at non-decreasing rows, so the run is an interval)
     const int tid = threadIdx.x, nt = blockDim.x;
     const int ext = ctl->wmax[0] - ctl->wmin[0] + 1;
-    for (int h = 0; h < P.n_heads; ++h) {
-        float *w = &tt[h].w[0][0];
-        for (int i = tid; i < ext * kPBwd; i += nt) w[i] = 0.f;
+    for (int h = 0; h < P.n_heads; ++h)
         for (int i = tid; i < ext; i += nt) { tt[h].pa[i] = 0x7fffffff; tt[h].pb[i] = 0; }
-    }
     __syncthreads();
     int base = 0;
     for (int h = 0; h < P.n_heads; ++h) {
@@ -535,15 +540,9 @@ __device__ __forceinline__ void build_ttabs(const KParams &P, const BlockCtl *ct
             const AxisTab &t = ctl->hd[h].tab[0];
             TTab &T = tt[h];
             const int n = t.n[p], row0 = t.lo[p] - ctl->wmin[0];
-            const float4 w4 = t.w[p];
-            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-            for (int k = 0; k < kNT; ++k) {
-                if (k < n) {
-                    T.w[row0 + k][p] = wv[k];
-                    atomicMin(&T.pa[row0 + k], p);
-                    atomicMax(&T.pb[row0 + k], p + 1);
-                }
+            for (int k = 0; k < n; ++k) {
+                atomicMin(&T.pa[row0 + k], p);
+                atomicMax(&T.pb[row0 + k], p + 1);
             }
         }
         base += P.PH[h];
@@ -640,7 +639,8 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
             for (int pw0 = 0; pw0 < PW; pw0 += kZ) {
                 float4 Z[kZ], v[kZ];
                 const float *g = gbase + (size_t)pw0 * C;
-                const float *wrow = &Ty.w[i][0];
+                const AxisTab &ytab = ctl->hd[h].tab[0];
+                const int yrow = y0 + i;
                 auto load_bins = [&](float4 (&dst)[kZ], const float *src) {
 #pragma unroll
                     for (int k = 0; k < kZ; ++k) {
@@ -658,7 +658,7 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
                 load_bins(Z, g);
                 load_bins(v, g + (two ? gstep : 0));
                 {
-                    const float w0 = wrow[pa], w1 = two ? wrow[pa + 1] : 0.f;
+                    const float w0 = wy_of(ytab, pa, yrow), w1 = two ? wy_of(ytab, pa + 1, yrow) : 0.f;
 #pragma unroll
                     for (int k = 0; k < kZ; ++k) {
                         Z[k] = mul4(w0, Z[k]);
@@ -667,7 +667,7 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
                 }
                 g += 2 * (size_t)gstep;
                 for (int ph = pa + 2; ph < pb; ++ph, g += gstep) {
-                    const float w = wrow[ph];
+                    const float w = wy_of(ytab, ph, yrow);
                     load_bins(v, g);
 #pragma unroll
                     for (int k = 0; k < kZ; ++k) fma4(Z[k], w, v[k]);
@@ -726,7 +726,7 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockCtl *ctl = reinterpret_cast<BlockCtl *>(smem_raw);
-    constexpr int kCtlBytes = (sizeof(BlockCtl) + 127) & ~127;
+    const int kCtlBytes = (rec_bytes(P.n_heads) + 127) & ~127;   // only this launch's head parts are loaded
     constexpr int kTTabBytes = (sizeof(TTab) + 127) & ~127;
     TTab *tt = reinterpret_cast<TTab *>(smem_raw + kCtlBytes);
 
