@@ -13,7 +13,8 @@
  *     - the heads' per-RoI dispatch loops that call them once per RoI
  *       (chainer_maskrcnn/model/head/fpn_roi_mask_head.py:57-63,74-78,90-95;
  *        fpn_roi_keypoint_head.py:59-71,83-87,99-104)
- *     with ONE launch per direction over the whole pyramid and all heads.
+ *     with ONE launch per direction over the whole pyramid and all heads (the
+ *     backward pass of a two-size problem runs one launch per pooled size).
  *   rpool_assign_levels replaces map_rois_to_fpn_levels
  *       (chainer_maskrcnn/model/rpn/multilevel_region_proposal_network.py:16-31)
  *       plus the clip at chainer_maskrcnn/model/maskrcnn.py:141.
