@@ -99,6 +99,18 @@ class ROIAlign2D(object):
         top, = self.forward_gpu((_host.h2d(x), _host.h2d(rois)))
         return _host.d2h(top),
 
+    def forward_cpu2(self, inputs):
+        """The reference's C++-port entry (roi_align_2d.py:34-37 ->
+        caffe2_roi_align.forward, caffe2_roi_align.cpp:231-243): caffe2 sampling
+        semantics with sampling_ratio fixed to 1 (:240), whatever this object's own
+        sampling_ratio is.  Host arrays in, host array out, computed on the GPU."""
+        self.check_type_forward(inputs)
+        x, rois = inputs
+        (top,), _ = _engine.forward([_host.h2d(x)], _host.h2d(rois), None, [self.spatial_scale],
+                                    [(self.outh, self.outw)], sampling_ratio=1,
+                                    coord_mode=_lib.COORD_CAFFE2, roi_format=_lib.ROI_XY)
+        return _host.d2h(top),
+
     def backward_cpu(self, inputs, gy):
         rois = _host.h2d(inputs[1])
         g = _host.h2d(gy[0])

@@ -78,6 +78,18 @@ def test_host_arrays_roundtrip_through_gpu():
     assert np.array_equal(np.asarray(y3), np.asarray(y))
 
 
+def test_forward_cpu2_is_the_cpp_port_entry():
+    # roi_align_2d.py:34-37: caffe2 semantics, sampling_ratio 1 (caffe2_roi_align.cpp:240)
+    x, rois, gy, outh, outw, scale = _fixture(seed=2)
+    f = ROIAlign2D(outh, outw, scale, sampling_ratio=2)        # its own ratio is not used by this entry
+    y, = f.forward_cpu2((x, rois))
+    assert isinstance(y, np.ndarray) and y.shape == (rois.shape[0], x.shape[1], outh, outw)
+    want = oracle.forward_caffe2(x, rois, outh, outw, scale, 1)
+    assert oracle.rel_err(y, want) <= 1e-5
+    if oracle.have_ref():                                      # the reference's own compiled C++
+        assert oracle.rel_err(y, oracle.ref_caffe2_forward(x, rois, outh, outw, scale, 1)) <= 1e-5
+
+
 def test_yx_wrapper_equals_permuted_call():
     x, rois, gy, outh, outw, scale = _fixture()
     yx = rois[:, [0, 2, 1, 4, 3]].copy()

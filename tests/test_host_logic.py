@@ -30,7 +30,8 @@ def test_reference_names_and_signatures():
     sig = inspect.signature(map_rois_to_fpn_levels)
     assert list(sig.parameters) == ["rois", "k_min", "k_max"]
     assert sig.parameters["k_min"].default == 0 and sig.parameters["k_max"].default == 4
-    for m in ("check_type_forward", "forward_cpu", "forward_gpu", "backward_cpu", "backward_gpu"):
+    for m in ("check_type_forward", "forward_cpu", "forward_cpu2", "forward_gpu", "backward_cpu",
+              "backward_gpu"):
         assert callable(getattr(ROIAlign2D, m))
     assert list(inspect.signature(pkg.FPNRoIPooling.__call__).parameters)[:5] == \
         ["self", "x", "indices_and_rois", "levels", "spatial_scales"]
