@@ -52,7 +52,7 @@ def _image_groups(indices_and_rois, n_images, max_groups=4):
     import numpy as np
     R = indices_and_rois.shape[0]
     whole = [(0, n_images, 0, R)]
-    if n_images < 2 or R == 0:
+    if n_images < 2 or R == 0 or max_groups < 2:
         return whole
     img = indices_and_rois[:, 0]
     if not (np.all(img[1:] >= img[:-1]) and img[0] >= 0 and img[-1] < n_images
@@ -66,7 +66,7 @@ def _image_groups(indices_and_rois, n_images, max_groups=4):
 
 
 def fpn_roi_align_host(x, indices_and_rois, levels, spatial_scales, out_sizes,
-                       sampling_ratio=1, gys=None):
+                       sampling_ratio=1, gys=None, max_groups=4):
     """Same call on NumPy host arrays (NCHW float32, as the reference holds them):
     every array is copied to the GPU, pooled there and copied back.  With ``gys``
     (one upstream gradient per pooled size) the backward pass runs too.
@@ -91,7 +91,7 @@ def fpn_roi_align_host(x, indices_and_rois, levels, spatial_scales, out_sizes,
     x = [np.asarray(f) for f in x]
     rois_h = np.ascontiguousarray(indices_and_rois, dtype=np.float32)
     N, C, R = x[0].shape[0], x[0].shape[1], rois_h.shape[0]
-    groups = _image_groups(rois_h, N)
+    groups = _image_groups(rois_h, N, max_groups)
 
     def keep(t, *streams):          # tensors cross streams: tell the caching allocator
         for st in streams:

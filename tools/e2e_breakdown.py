@@ -33,4 +33,10 @@ res["d2h_pooled_ms"] = T(lambda: _host.d2h(outs[0]))
 def full():
     p, g = pkg.fpn_roi_align_host(feats, rois_p, None, scales, [14], 2, gys=[gy]); del p, g
 res["full_ms"] = T(full)
+def full1():
+    p, g = pkg.fpn_roi_align_host(feats, rois_p, None, scales, [14], 2, gys=[gy], max_groups=1); del p, g
+res["full_single_group_ms"] = T(full1)
+res["full_ms_20"] = T(full, 20)
+res["full_single_group_ms_20"] = T(full1, 20)
+res["full_ms_20_again"] = T(full, 20)
 print(json.dumps(res))
