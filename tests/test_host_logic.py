@@ -89,6 +89,45 @@ def test_sharding_by_image():
     assert _sharding.max_over_ranks(3.5) == 3.5
 
 
+def test_host_call_groups_images_only_when_rois_are_image_major():
+    from chainer_maskrcnn_b200.functions.fpn_roi_align import _image_groups
+    r = np.zeros((10, 5), np.float32)
+    r[:, 0] = [0, 0, 0, 1, 1, 2, 2, 2, 2, 3]
+    assert _image_groups(r, 4) == [(0, 1, 0, 3), (1, 2, 3, 5), (2, 3, 5, 9), (3, 4, 9, 10)]
+    # more images than groups: contiguous image ranges; images without RoIs get empty row ranges
+    g = _image_groups(r, 8)
+    assert [x[:2] for x in g] == [(0, 2), (2, 4), (4, 6), (6, 8)]
+    assert [x[2:] for x in g] == [(0, 5), (5, 10), (10, 10), (10, 10)]
+    assert _image_groups(r, 4, max_groups=1) == [(0, 4, 0, 10)]
+    assert _image_groups(r, 1) == [(0, 1, 0, 10)]
+    assert _image_groups(r[:0], 4) == [(0, 4, 0, 0)]
+    for bad in ([0, 1, 0, 1, 1, 2, 2, 2, 2, 3], [0, 0, 0, 1, 1, 2, 2, 2, 2, 4], [0, 0, 0, 1, 1, 2, 2, 2, 2, 2.5]):
+        r2 = r.copy()
+        r2[:, 0] = bad
+        assert _image_groups(r2, 4) == [(0, 4, 0, 10)]        # interleaved / out of range / fractional
+
+
+def test_bench_sharded_workload_covers_every_roi_once():
+    # bench.py --shard: ONE instance of the config, images dealt round-robin to the ranks
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth
+    cfg = synth.CONFIGS[3]
+    rng = np.random.RandomState(3)
+    rois = synth.make_rois(rng, cfg["n_images"], cfg["rois_per_image"], cfg["height"], cfg["width"],
+                           aspect_range=cfg["aspect"])
+    for world in (2, 4, 8):
+        seen, n_img = [], 0
+        for rank in range(world):
+            local, rows = _sharding.shard_rois(rois, cfg["n_images"], world, rank)
+            mine = _sharding.images_of_rank(cfg["n_images"], world, rank)
+            n_img += len(mine)
+            assert local[:, 0].max() == len(mine) - 1 and local[:, 0].min() == 0
+            assert np.array_equal(local[:, 1:], rois[rows, 1:])
+            seen.append(rows)
+        assert n_img == cfg["n_images"]
+        assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(rois.shape[0]))
+
+
 _WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})
