@@ -107,6 +107,19 @@ def test_host_call_groups_images_only_when_rois_are_image_major():
         assert _image_groups(r2, 4) == [(0, 4, 0, 10)]        # interleaved / out of range / fractional
 
 
+def test_channel_padding_helper_and_plan_fields():
+    # channel counts that are not a multiple of 4 are zero-extended by the shim (the light
+    # head's 490-channel map): layout, values and padding of the helper, on CPU tensors
+    t = torch.randn(2, 6, 5, 7)
+    o = _engine._pad_channels(t, 8)
+    assert tuple(o.shape) == (2, 8, 5, 7) and o.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(o[:, :6], t) and float(o[:, 6:].abs().max()) == 0.0
+    assert tuple(_engine._pad_channels(torch.randn(0, 6, 5, 7), 8).shape) == (0, 8, 5, 7)
+    assert "cpad" in _engine.Plan.__slots__ and "problem" in _engine.Plan.__slots__
+    with pytest.raises(TypeError):
+        _engine.make_plan([(1, 6, 8, 8)], torch.zeros(3, 5), None, [0.25], [7])      # CPU RoIs: no fallback
+
+
 def test_bench_sharded_workload_covers_every_roi_once():
     # bench.py --shard: ONE instance of the config, images dealt round-robin to the ranks
     sys.path.insert(0, os.path.join(ROOT, "tests"))
