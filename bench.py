@@ -379,7 +379,10 @@ def run_reference(args):
         return
     import oracle
     oracle.build()
-    sample = args.cpu_sample_rois if args.cpu_sample_rois > 0 else 1024
+    # bounded sample per step, sized so that the whole --steps K run stays within a few minutes
+    # on the host cores (the port does ~5 k RoIs/s on 16 cores: about 60 s of work in total)
+    sample = args.cpu_sample_rois if args.cpu_sample_rois > 0 else \
+        min(1024, max(64, 300000 // max(args.steps, 1)))
     for _ in range(max(args.warmup, 0) and 1):
         cpu_arm(args.config, args.sampling_ratio, min(sample, 64))
     vals, info = [], None
