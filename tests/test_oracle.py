@@ -85,6 +85,63 @@ def test_caffe2_restatement_equals_reference_cpp_bitwise(S, outh, outw):
     assert np.array_equal(oracle.forward_caffe2(x, rois, outh, outw, scale, S, threads=4), b)
 
 
+# ---- 2b. randomised sweeps against the reference itself ----------------------
+def _sweep_case(seed):
+    rng = np.random.RandomState(9000 + seed)
+    N, C = int(rng.randint(1, 4)), int(rng.randint(1, 9))
+    H, W = int(rng.randint(4, 40)), int(rng.randint(4, 40))
+    scale = float(rng.choice([1.0, 0.5, 0.25, 0.125, 0.6, 1.0 / 3.0]))
+    outh, outw = int(rng.randint(1, 16)), int(rng.randint(1, 16))
+    R = int(rng.randint(1, 40))
+    x = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    # boxes inside the map (the parity domain of the NumPy path), some of them degenerate
+    b = rng.randint(0, N, R).astype(np.float32)
+    x1 = rng.uniform(0, (W - 1) / scale, R)
+    y1 = rng.uniform(0, (H - 1) / scale, R)
+    x2 = x1 + rng.uniform(0, 1, R) * ((W - 1) / scale - x1)
+    y2 = y1 + rng.uniform(0, 1, R) * ((H - 1) / scale - y1)
+    deg = rng.rand(R) < 0.15
+    x2[deg] = x1[deg]
+    rois = np.stack([b, x1, y1, x2, y2], 1).astype(np.float32)
+    return rng, x, rois, outh, outw, scale
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", range(24))
+def test_random_sweep_chainer_path_equals_reference_bitwise(seed):
+    rng, x, rois, outh, outw, scale = _sweep_case(seed)
+    try:
+        y_ref = ref.reference_forward(x, rois, outh, outw, scale)
+    except IndexError:
+        with pytest.raises(IndexError):
+            oracle.forward_chainer(x, rois, outh, outw, scale)
+        return
+    y = oracle.forward_chainer(x, rois, outh, outw, scale)
+    assert np.array_equal(y, y_ref)
+    gy = rng.uniform(-1, 1, y.shape).astype(np.float32)
+    assert np.array_equal(oracle.backward_chainer(gy, rois, x.shape, scale),
+                          ref.reference_backward(gy, x, rois, outh, outw, scale))
+
+
+@needs_ref_cpp
+@pytest.mark.parametrize("seed", range(24))
+def test_random_sweep_caffe2_restatement_equals_reference_cpp_bitwise(seed):
+    rng, x, rois, outh, outw, scale = _sweep_case(seed)
+    # caffe2 semantics are defined beyond the map: push some boxes over the borders
+    k = rng.rand(rois.shape[0]) < 0.3
+    rois[k, 1:3] -= rng.uniform(0, 20, (int(k.sum()), 2)).astype(np.float32)
+    rois[k, 3:5] += rng.uniform(0, 20, (int(k.sum()), 2)).astype(np.float32)
+    S = int(rng.choice([0, 1, 2, 3, 4]))
+    a = oracle.forward_caffe2(x, rois, outh, outw, scale, S)
+    assert np.array_equal(a, oracle.ref_caffe2_forward(x, rois, outh, outw, scale, S))
+    # its backward is defined as the adjoint of that forward: <y, gy> == <x, gx>
+    gy = rng.uniform(-1, 1, a.shape).astype(np.float32)
+    gx = oracle.backward_caffe2(gy, rois, x.shape, scale, S)
+    lhs = float(np.sum(a.astype(np.float64) * gy))
+    rhs = float(np.sum(x.astype(np.float64) * gx))
+    assert abs(lhs - rhs) <= 1e-3 * max(1.0, abs(lhs))
+
+
 # ---- 3. golden vectors -------------------------------------------------------
 def test_golden_reference_fixture(golden_dir):
     d = _load(golden_dir, "reference_fixture.npz")
