@@ -111,12 +111,50 @@ def level_vectors():
                 thresholds=oracle.level_area_thresholds())
 
 
+def sweep(n_cases=8):
+    """Random small single-level cases (odd channel counts, rectangular outputs, maps
+    narrower than the vectorised path needs, degenerate boxes): the reference NumPy op
+    forward/backward on in-bounds boxes, and the reference C++ forward at a random
+    sampling grid on the same boxes pushed over the borders."""
+    out = dict(n_cases=np.int32(n_cases))
+    for i in range(n_cases):
+        rng = np.random.RandomState(4200 + i)
+        N, C = int(rng.randint(1, 3)), int(rng.randint(1, 7))
+        H, W = int(rng.randint(5, 33)), int(rng.randint(5, 33))
+        scale = float(rng.choice([1.0, 0.5, 0.25, 0.6]))
+        outh, outw = int(rng.randint(1, 15)), int(rng.randint(1, 15))
+        R = int(rng.randint(2, 13))
+        x = rng.standard_normal((N, C, H, W)).astype(np.float32)
+        b = rng.randint(0, N, R).astype(np.float32)
+        x1 = rng.uniform(0, (W - 1) / scale, R)
+        y1 = rng.uniform(0, (H - 1) / scale, R)
+        x2 = x1 + rng.uniform(0, 1, R) * ((W - 1) / scale - x1)
+        y2 = y1 + rng.uniform(0, 1, R) * ((H - 1) / scale - y1)
+        x2[0], y2[0] = x1[0], y1[0]                                   # a degenerate box
+        rois = np.stack([b, x1, y1, x2, y2], 1).astype(np.float32)
+        gy = rng.uniform(-1, 1, (R, C, outh, outw)).astype(np.float32)
+        S = int(rng.choice([0, 1, 2, 3]))
+        rois_c2 = rois.copy()
+        k = rng.rand(R) < 0.4
+        rois_c2[k, 1:3] -= rng.uniform(0, 10, (int(k.sum()), 2)).astype(np.float32)
+        rois_c2[k, 3:5] += rng.uniform(0, 10, (int(k.sum()), 2)).astype(np.float32)
+        pre = "c%d_" % i
+        out.update({pre + "x": x, pre + "rois": rois, pre + "gy": gy,
+                    pre + "geom": np.array([outh, outw, S], np.int32), pre + "scale": np.float32(scale),
+                    pre + "y": ref.reference_forward(x, rois, outh, outw, scale),
+                    pre + "gx": ref.reference_backward(gy, x, rois, outh, outw, scale),
+                    pre + "rois_c2": rois_c2,
+                    pre + "y_c2": oracle.ref_caffe2_forward(x, rois_c2, outh, outw, scale, S)})
+    return out
+
+
 def main():
     assert ref.available(), "needs the reference tree"
     assert oracle.have_ref() or (oracle.build() or oracle.have_ref())
     np.savez_compressed(os.path.join(HERE, "reference_fixture.npz"), **reference_fixture())
     np.savez_compressed(os.path.join(HERE, "fpn_small.npz"), **fpn_small())
     np.savez_compressed(os.path.join(HERE, "levels.npz"), **level_vectors())
+    np.savez_compressed(os.path.join(HERE, "sweep.npz"), **sweep())
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -134,6 +134,28 @@ def test_golden_fpn_small_fused_two_heads(golden_dir):
     assert oracle.rel_err(outs[1], d["y14_caffe2_s2"]) <= FWD_TOL
 
 
+def test_golden_sweep_single_level_op(golden_dir):
+    # random small cases from the reference itself (odd channel counts, rectangular outputs,
+    # narrow maps, degenerate boxes; C++ forward with boxes over the borders)
+    from chainer_maskrcnn_b200 import ROIAlign2D
+    d = np.load(os.path.join(golden_dir, "sweep.npz"))
+    for i in range(int(d["n_cases"])):
+        g = lambda k: d["c%d_%s" % (i, k)]
+        outh, outw, S = (int(v) for v in g("geom"))
+        scale = float(g("scale"))
+        x, rois = dev(g("x")), dev(g("rois"))
+        f = ROIAlign2D(outh, outw, scale)
+        (y,) = f.forward_gpu((x, rois))
+        assert tuple(y.shape) == g("y").shape
+        assert oracle.rel_err(host(y), g("y")) <= FWD_TOL, i
+        gx, _ = f.backward_gpu((None, rois), (dev(g("gy")),))
+        assert tuple(gx.shape) == g("x").shape
+        assert oracle.rel_err(host(gx), g("gx")) <= BWD_TOL, i
+        (y2,), _ = _engine.forward([x], dev(g("rois_c2")), None, [scale], [(outh, outw)], S,
+                                   _lib.COORD_CAFFE2, _lib.ROI_XY)
+        assert oracle.rel_err(host(y2), g("y_c2")) <= FWD_TOL, (i, S)
+
+
 def test_golden_levels_bit_exact(golden_dir):
     d = np.load(os.path.join(golden_dir, "levels.npz"))
     got = host(_engine.assign_levels(dev(d["boxes"])))

@@ -174,6 +174,18 @@ def test_golden_fpn_small(golden_dir):
         assert np.array_equal(y2, d["y%d_caffe2_s2" % P])
 
 
+def test_golden_sweep(golden_dir):
+    # random small cases generated from the reference (tests/golden/make_golden.py: sweep)
+    d = _load(golden_dir, "sweep.npz")
+    for i in range(int(d["n_cases"])):
+        g = lambda k: d["c%d_%s" % (i, k)]
+        outh, outw, S = (int(v) for v in g("geom"))
+        scale = float(g("scale"))
+        assert np.array_equal(oracle.forward_chainer(g("x"), g("rois"), outh, outw, scale), g("y")), i
+        assert np.array_equal(oracle.backward_chainer(g("gy"), g("rois"), g("x").shape, scale), g("gx")), i
+        assert np.array_equal(oracle.forward_caffe2(g("x"), g("rois_c2"), outh, outw, scale, S), g("y_c2")), i
+
+
 def test_golden_levels(golden_dir):
     d = _load(golden_dir, "levels.npz")
     assert np.array_equal(oracle.map_rois_to_fpn_levels(d["boxes"]), d["levels"])
