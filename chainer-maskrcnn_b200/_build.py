@@ -1,5 +1,6 @@
 """In-tree build of librpool_b200.so with nvcc for sm_100a (no JIT cache: the
 built file sits next to this package so that it travels with the tree)."""
+import hashlib
 import os
 import shutil
 import subprocess
@@ -26,19 +27,41 @@ def _nvcc():
     raise RuntimeError("nvcc not found; cannot build librpool_b200.so")
 
 
+def sources_present():
+    return all(os.path.exists(os.path.join(CSRC, f)) for f in SOURCES + HEADERS)
+
+
+def source_hash():
+    """Build id: sha1 over the sources and headers the library is compiled from."""
+    h = hashlib.sha1()
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+ID_PATH = LIB_PATH + ".id"
+
+
 def is_stale():
+    """True when the library is missing or was built from other sources (the build id of
+    the last build is kept beside it: file times do not survive a copy of the tree)."""
     if not os.path.exists(LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+    if not sources_present():
+        return False
+    try:
+        with open(ID_PATH) as f:
+            return f.read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force=False, verbose=False):
     """Compile csrc/*.cu -> librpool_b200.so.  Returns the library path."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS
+    cmd = [_nvcc()] + NVCC_FLAGS + ['-DRPOOL_BUILD_ID="%s"' % source_hash()]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
@@ -47,6 +70,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stdout))
     if verbose:
         print(proc.stdout)
+    with open(ID_PATH, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB_PATH
 
 

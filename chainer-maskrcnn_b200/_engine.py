@@ -63,6 +63,25 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _NoGuard(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on(device):
+    """Device guard for the launches: nothing when `device` is already current (the
+    usual case; the torch guard costs several microseconds per call)."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
+
+
 def _require_cuda(t, name):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise TypeError("%s must be a CUDA torch.Tensor (there is no CPU fallback)" % name)
@@ -80,7 +99,8 @@ def to_channels_last(t):
     src = t.contiguous()
     n, c, h, w = src.shape
     dst = torch.empty_like(src, memory_format=torch.channels_last)
-    _lib.check(_lib.lib().rpool_nchw_to_nhwc(src.data_ptr(), dst.data_ptr(), n, c, h, w, _stream()))
+    with _on(t.device):     # launch on the tensor's device and its current stream
+        _lib.check(_lib.lib().rpool_nchw_to_nhwc(src.data_ptr(), dst.data_ptr(), n, c, h, w, _stream()))
     return dst
 
 
@@ -102,7 +122,8 @@ def to_nchw_contiguous(t):
         t = to_channels_last(t)
     n, c, h, w = t.shape
     dst = torch.empty((n, c, h, w), dtype=t.dtype, device=t.device)
-    _lib.check(_lib.lib().rpool_nhwc_to_nchw(t.data_ptr(), dst.data_ptr(), n, c, h, w, _stream()))
+    with _on(t.device):
+        _lib.check(_lib.lib().rpool_nhwc_to_nchw(t.data_ptr(), dst.data_ptr(), n, c, h, w, _stream()))
     return dst
 
 
@@ -110,26 +131,7 @@ class Plan(object):
     """Everything backward needs: geometry, RoIs, the device schedule."""
     __slots__ = ("shapes", "scales", "rois", "levels_i32", "levels_f32", "thresholds", "k_min",
                  "out_sizes", "sampling_ratio", "coord_mode", "roi_format", "workspace",
-                 "channels", "cpad", "device", "problem")
-
-
-class _NoGuard(object):
-    def __enter__(self):
-        return self
-
-    def __exit__(self, *exc):
-        return False
-
-
-_NO_GUARD = _NoGuard()
-
-
-def _on(device):
-    """Device guard for the launches: nothing when `device` is already current (the
-    usual case; the torch guard costs several microseconds per call)."""
-    if device.index is None or device.index == torch.cuda.current_device():
-        return _NO_GUARD
-    return torch.cuda.device(device)
+                 "channels", "cpad", "device", "problem", "options")
 
 
 def _fill_problem(plan, level_ptrs, pooled_ptrs, accumulate=False, deterministic=False):
@@ -176,6 +178,7 @@ def _fill_problem(plan, level_ptrs, pooled_ptrs, accumulate=False, deterministic
     p.coord_mode = plan.coord_mode
     p.accumulate = int(accumulate)
     p.deterministic = int(deterministic)
+    p.opt = _lib.make_options(**plan.options)
     return p
 
 
@@ -196,10 +199,12 @@ def default_coord_mode(sampling_ratio):
 
 
 def make_plan(shapes, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
-              coord_mode=None, roi_format=_lib.ROI_YX, k_min=0, k_max=4, pad_channels=True):
+              coord_mode=None, roi_format=_lib.ROI_YX, k_min=0, k_max=4, pad_channels=True,
+              options=None, workspace=None):
     """Validates the call, assigns levels (when not given) and bins the RoIs by
     (image, level) on the device: one small launch (rpool_plan).  The Plan is
-    all that forward and backward share."""
+    all that forward and backward share.  ``options``: rpool_options fields by name
+    (experiments; defaults otherwise).  ``workspace``: a uint8 CUDA tensor to reuse."""
     shapes = [tuple(int(v) for v in s) for s in shapes]
     if not 1 <= len(shapes) <= _lib.MAX_LEVELS:
         raise ValueError("pyramid must have 1..%d levels" % _lib.MAX_LEVELS)
@@ -218,6 +223,7 @@ def make_plan(shapes, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
 
     plan = Plan()
     plan.problem = None
+    plan.options = dict(options or {})
     plan.device = rois.device
     plan.shapes = shapes
     plan.scales = [float(s) for s in spatial_scales]
@@ -230,12 +236,15 @@ def make_plan(shapes, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
             raise TypeError("levels must be a CUDA tensor or None")
         if tuple(levels.shape) != (rois.shape[0],):
             raise ValueError("levels must have shape (R,)")
-        if levels.dtype == torch.int32:
-            plan.levels_i32 = levels.contiguous()
-        elif levels.dtype == torch.float32:
-            plan.levels_f32 = levels.contiguous()
+        if levels.dtype == torch.float32:
+            plan.levels_f32 = levels.contiguous()       # map_rois_to_fpn_levels' own dtype
+        elif levels.dtype in (torch.float64, torch.float16, torch.bfloat16):
+            plan.levels_f32 = levels.to(torch.float32).contiguous()
+        elif levels.dtype == torch.bool or levels.dtype.is_complex:
+            raise TypeError("levels must be an integer or floating tensor, got %s" % levels.dtype)
         else:
-            raise TypeError("levels must be int32 or float32 (map_rois_to_fpn_levels returns float32)")
+            # the heads cast with astype(int32) (fpn_roi_mask_head.py:58): any integer dtype will do
+            plan.levels_i32 = levels.to(torch.int32).contiguous()
     elif len(shapes) > 1:
         plan.thresholds = level_thresholds(k_min, k_max)
     plan.out_sizes = _norm_sizes(out_sizes)
@@ -250,7 +259,13 @@ def make_plan(shapes, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
 
     L = _lib.lib()
     ws_bytes = L.rpool_workspace_bytes_ex(rois.shape[0], len(plan.out_sizes), plan.coord_mode)
-    plan.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=rois.device)
+    if workspace is not None:
+        if workspace.dtype != torch.uint8 or workspace.device != rois.device or workspace.numel() < ws_bytes:
+            raise ValueError("workspace must be a uint8 tensor of >= %d bytes on %s" % (ws_bytes, rois.device))
+        plan.workspace = workspace
+    else:
+        plan.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=rois.device)
+    ws_bytes = plan.workspace.numel()
     # rpool_plan reads geometry only; level/pooled addresses are not dereferenced
     dummy = plan.workspace.data_ptr()
     prob = _fill_problem(plan, [dummy] * len(shapes), [None] * len(plan.out_sizes))
@@ -260,23 +275,36 @@ def make_plan(shapes, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
 
 
 def forward(features, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
-            coord_mode=None, roi_format=_lib.ROI_YX, k_min=0, k_max=4, plan=None, pad_channels=True):
+            coord_mode=None, roi_format=_lib.ROI_YX, k_min=0, k_max=4, plan=None, pad_channels=True,
+            options=None, workspace=None, out=None):
     """One fused launch over the pyramid.  Returns ([pooled per head], Plan).
 
     features: sequence of logical (N,C,H_l,W_l) float32 CUDA tensors;
     rois: (R,5) float32 CUDA tensor; levels: None (assigned on the device by the
-    reference rule, clipped to the pyramid), or an int32/float32 CUDA tensor (R,).
+    reference rule, clipped to the pyramid), or an integer/floating CUDA tensor (R,).
+    ``out``: optional preallocated channels-last (R,C,oh,ow) tensors to write into.
     """
     features = list(features)
     for i, f in enumerate(features):
         _require_cuda(f, "features[%d]" % i)
     if plan is None:
         plan = make_plan([f.shape for f in features], rois, levels, spatial_scales, out_sizes,
-                         sampling_ratio, coord_mode, roi_format, k_min, k_max, pad_channels)
+                         sampling_ratio, coord_mode, roi_format, k_min, k_max, pad_channels,
+                         options, workspace)
     R, C, Cp = plan.rois.shape[0], plan.channels, plan.cpad
+    for i, f in enumerate(features):
+        if f.device != plan.device:
+            raise ValueError("features[%d] is on %s, the RoIs are on %s" % (i, f.device, plan.device))
     feats = [to_channels_last(f) if Cp == C else _pad_channels(f, Cp) for f in features]
-    outs = [torch.empty((R, Cp, oh, ow), dtype=torch.float32, device=plan.device,
-                        memory_format=torch.channels_last) for oh, ow in plan.out_sizes]
+    if out is not None and Cp == C:
+        outs = list(out)
+        for o, (oh, ow) in zip(outs, plan.out_sizes):
+            if tuple(o.shape) != (R, C, oh, ow) or not o.is_contiguous(memory_format=torch.channels_last) \
+                    or o.dtype != torch.float32 or o.device != plan.device:
+                raise ValueError("out tensors must be float32 channels-last (R,C,oh,ow) on the RoIs' device")
+    else:
+        outs = [torch.empty((R, Cp, oh, ow), dtype=torch.float32, device=plan.device,
+                            memory_format=torch.channels_last) for oh, ow in plan.out_sizes]
     prob = _fill_problem(plan, [f.data_ptr() for f in feats], [o.data_ptr() for o in outs])
     with _on(plan.device):
         _lib.check(_lib.lib().rpool_forward(ctypes.byref(prob), plan.workspace.data_ptr(),
@@ -336,11 +364,11 @@ def backward(plan, gys, deterministic=False, out=None, accumulate=False):
         _lib.check(L.rpool_backward(ctypes.byref(prob), ws, ws_n, _stream()))
         if deterministic:
             err = ctypes.c_int32(0)
-            _lib.check(L.rpool_det_status(ws, R, _stream(), ctypes.byref(err)))
-            if err.value:
+            _lib.check(L.rpool_status_flags(ws, R, _stream(), ctypes.byref(err)))
+            if err.value & (_lib.FLAG_DET_GENERIC | _lib.FLAG_DET_SCRATCH):
                 raise _lib.RpoolError(_lib.UNSUPPORTED, "deterministic backward: some RoIs need the generic "
                                       "kernel path (pooled size > 16, sampling grid > 4, window taller "
-                                      "than 64 rows or map narrower than 8 columns); status %d" % err.value)
+                                      "than 64 rows or map narrower than 8 columns); flags %d" % err.value)
     if padded:
         C = plan.channels
         if user_out is None:
@@ -365,6 +393,44 @@ def read_plan(plan):
     return lv, od
 
 
+def status_flags(plan):
+    """RPOOL_FLAG_* bits raised for this plan's RoIs (synchronises the current stream).
+    The reference's NumPy path raises IndexError for a RoI whose batch index or taps
+    leave the tensor (roi_align_2d.py:76-86); the kernels compute zeros / clamp instead
+    and flag it here."""
+    flags = ctypes.c_int32(0)
+    with _on(plan.device):
+        _lib.check(_lib.lib().rpool_status_flags(plan.workspace.data_ptr(), plan.rois.shape[0],
+                                                 _stream(), ctypes.byref(flags)))
+    return flags.value
+
+
+def check_rois(plan):
+    """Raises IndexError, like the reference's NumPy path, when a RoI addressed an image
+    outside the batch (synchronises the current stream)."""
+    if status_flags(plan) & _lib.FLAG_BAD_BATCH:
+        raise IndexError("a RoI's batch index is outside [0, n_images)")
+
+
+def zero_fill(grads):
+    """Zero fill of channels-last gradient tensors (one launch for all levels) on the
+    current stream: rpool_backward's first step, callable early on another stream."""
+    grads = list(grads)
+    if not grads:
+        return
+    p = _lib.Problem()
+    p.n_levels = len(grads)
+    p.channels = grads[0].shape[1]
+    for l, g in enumerate(grads):
+        _require_cuda(g, "grads[%d]" % l)
+        if not g.is_contiguous(memory_format=torch.channels_last) or g.shape[1] != p.channels:
+            raise ValueError("gradients must be channels-last tensors with one channel count")
+        p.level[l].data = g.data_ptr()
+        p.level[l].n_images, p.level[l].height, p.level[l].width = g.shape[0], g.shape[2], g.shape[3]
+    with _on(grads[0].device):
+        _lib.check(_lib.lib().rpool_zero_fill(ctypes.byref(p), _stream()))
+
+
 class _FPNRoIAlignFn(torch.autograd.Function):
     """autograd node: the analogue of the reference's ROIAlign2D Function objects
     (roi_align_2d.py:15), one per call instead of one per RoI."""
@@ -376,6 +442,7 @@ class _FPNRoIAlignFn(torch.autograd.Function):
         return tuple(outs)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, *gys):
         grads = backward(ctx.plan, list(gys))
         return (None, None, None) + tuple(grads)

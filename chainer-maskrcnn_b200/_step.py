@@ -1,0 +1,107 @@
+"""FusedStep -- one pooling step (plan + forward + backward) over static buffers.
+
+What a training loop does around the heads, packaged so that the launch overhead
+and the gradient zero fill leave the critical path:
+
+  * every buffer (plan workspace, pooled maps, dense gradients) is allocated once;
+  * the zero fill of the dense gradients depends on nothing, so it is forked to a
+    side stream where it overlaps rpool_plan and the start of rpool_forward, and
+    rpool_backward then runs with ``accumulate = 1`` (rpool_zero_fill in
+    include/rpool_b200.h exists for exactly this);
+  * with ``graph=True`` the whole step (fork and join included) is captured once
+    into a CUDA graph and replayed: the RoIs, features and upstream gradients are
+    read from their device buffers at replay time, so new data is written into the
+    same tensors (``step.rois.copy_(...)``) between replays.  Nothing on the path
+    synchronises with the host or sizes anything from device data.
+
+The reference has no counterpart: it dispatches two Chainer function calls per RoI
+(fpn_roi_mask_head.py:57-63,74-78).
+"""
+import torch
+
+from . import _engine, _lib
+
+
+class FusedStep(object):
+    """step = FusedStep(features, rois, levels, spatial_scales, out_sizes, sampling_ratio, gys)
+    step.run()            # plan + forward + backward on the current stream
+    step.outs, step.grads # pooled maps / dense feature gradients (channels-last), reused every run
+
+    features: list of float32 CUDA tensors (N,C,H_l,W_l), channels-last memory;
+    rois: (R,5) float32 [image, y1, x1, y2, x2]; levels: None (assigned on the device
+    by the reference rule) or an (R,) tensor; gys: one (R,C,P,P) channels-last upstream
+    gradient per pooled size (None: forward only)."""
+
+    def __init__(self, features, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
+                 gys=None, graph=True, deterministic=False, fork_zero_fill=True, options=None):
+        self.features = list(features)
+        self.rois, self.levels = rois, levels
+        self.scales = list(spatial_scales)
+        self.sizes = _engine._norm_sizes(out_sizes if isinstance(out_sizes, list) else [out_sizes])
+        self.sampling_ratio = int(sampling_ratio)
+        self.gys = None if gys is None else list(gys)
+        self.deterministic = bool(deterministic)
+        self.options = dict(options or {})
+        dev = rois.device
+        for i, f in enumerate(self.features):
+            _engine._require_cuda(f, "features[%d]" % i)
+            if not f.is_contiguous(memory_format=torch.channels_last) or f.shape[1] % 4:
+                raise ValueError("FusedStep needs channels-last features with C % 4 == 0 "
+                                 "(static buffers: no conversion or padding inside the step)")
+        R, C = rois.shape[0], self.features[0].shape[1]
+        self.outs = [torch.empty((R, C, oh, ow), dtype=torch.float32, device=dev,
+                                 memory_format=torch.channels_last) for oh, ow in self.sizes]
+        self.grads = None
+        if self.gys is not None:
+            self.grads = [torch.empty_like(f, memory_format=torch.channels_last) for f in self.features]
+        coord = _engine.default_coord_mode(self.sampling_ratio)
+        n = _lib.lib().rpool_workspace_bytes_ex(R, len(self.sizes), coord)
+        self.workspace = torch.empty(n, dtype=torch.uint8, device=dev)
+        # the deterministic variant sizes its scratch from the RoIs with a host round trip:
+        # it cannot fork the fill (it writes every cell itself) nor be captured
+        self.fork = bool(fork_zero_fill) and self.gys is not None and not self.deterministic
+        self._side = torch.cuda.Stream(device=dev) if self.fork else None
+        self.plan = None
+        self.graph = None
+        if graph and not self.deterministic:
+            self._capture()
+
+    # -- one step on the current stream ------------------------------------
+    def _launch(self):
+        with _engine._on(self.rois.device):
+            cur = torch.cuda.current_stream(self.rois.device)
+            ev = None
+            if self.fork:
+                self._side.wait_stream(cur)                      # fork
+                with torch.cuda.stream(self._side):
+                    _engine.zero_fill(self.grads)
+                    ev = self._side.record_event()
+            _, self.plan = _engine.forward(self.features, self.rois, self.levels, self.scales, self.sizes,
+                                           sampling_ratio=self.sampling_ratio, roi_format=_lib.ROI_YX,
+                                           options=self.options, workspace=self.workspace, out=self.outs)
+            if self.gys is not None:
+                if ev is not None:
+                    cur.wait_event(ev)                           # join
+                _engine.backward(self.plan, self.gys, out=self.grads, accumulate=self.fork,
+                                 deterministic=self.deterministic)
+
+    def _capture(self):
+        dev = self.rois.device
+        with _engine._on(dev):
+            warm = torch.cuda.Stream(device=dev)
+            warm.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(warm):
+                self._launch()        # shared-memory attributes and allocator state settle before capture
+            torch.cuda.current_stream(dev).wait_stream(warm)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch()
+            self.graph = g
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._launch()
+        return self.outs, self.grads

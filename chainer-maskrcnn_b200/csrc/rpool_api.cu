@@ -19,12 +19,23 @@ std::atomic<unsigned long long> g_launches{0};
 
 constexpr int kMaxSmem = 227 * 1024;
 
-// tuning knobs (process-wide; experiments only)
-std::atomic<int> g_prefetch{-3};
-std::atomic<int> g_threads{128};
-std::atomic<int> g_order{1};
-std::atomic<int> g_force_path{kPathAuto};
-std::atomic<int> g_split_heads{1};
+#ifndef RPOOL_BUILD_ID
+#define RPOOL_BUILD_ID "unknown"
+#endif
+
+// rpool_options with the defaults filled in (0 = default in the ABI)
+struct Options {
+    int threads, order, force_path, split_heads, prefetch, var_fwd, var_bwd;
+};
+constexpr int kDefaultThreads = 128;
+constexpr int kDefaultPrefetchRows = 2;
+constexpr int kVariantRows = 1, kVariantStream = 2;
+#ifndef RPOOL_DEFAULT_VARIANT_FWD
+#define RPOOL_DEFAULT_VARIANT_FWD 1
+#endif
+#ifndef RPOOL_DEFAULT_VARIANT_BWD
+#define RPOOL_DEFAULT_VARIANT_BWD 1
+#endif
 
 int fail(int code, const char *fmt, ...)
 {
@@ -46,25 +57,27 @@ int cuda_fail(cudaError_t e, const char *what)
         if (e__ != cudaSuccess) return cuda_fail(e__, what); \
     } while (0)
 
-// workspace layout (r = R rounded up to 32):
-//   int32  levels[r] order[r] keys[r] gstart[288] rects[4r]
+// workspace layout (r = R rounded up to 32, nb = key blocks of kKeyBlock RoIs):
+//   int32  levels[r] order[r] keys[r] rflags[r] gstart[288] bh[nb * 256] rects[4r]
 //   uint64 woff[r] sizes[r] det_total, then int32 det_err (+ padding to 16 bytes)
-//   RoI records (rpool_tables_kernel): one set of r records of rec_bytes(n_heads)
+//   RoI records (rpool_plan_kernel): one set of r records of rec_bytes(n_heads)
 //   for the forward geometry, and for RPOOL_COORD_CHAINER -- whose backward
 //   coordinates round differently (roi_align_2d.py:164-165) -- a second set
 constexpr size_t kGstartInts = 288;  // kPlanMaxKeys + 1, padded
 struct Workspace {
-    int *levels, *order, *keys, *gstart, *rects;
+    int *levels, *order, *keys, *rflags, *gstart, *bh, *rects;
     unsigned long long *woff, *sizes, *det_total;
     int *det_err;
     unsigned char *recs_fwd, *recs_bwd;
     int rec_stride;
 };
 size_t ws_round(int R) { return ((size_t)(R > 0 ? R : 1) + 31) & ~(size_t)31; }
+size_t ws_key_blocks(int R) { return ((size_t)(R > 0 ? R : 1) + kKeyBlock - 1) / kKeyBlock; }
 size_t ws_fixed_bytes(int R)
 {
     const size_t r = ws_round(R);
-    const size_t n = (3 * r + kGstartInts + 4 * r) * sizeof(int) + (2 * r + 1) * sizeof(unsigned long long) + 16;
+    const size_t n = (4 * r + kGstartInts + ws_key_blocks(R) * kPlanMaxKeys + 4 * r) * sizeof(int) +
+                     (2 * r + 1) * sizeof(unsigned long long) + 16;
     return (n + 15) & ~(size_t)15;
 }
 int rec_sets(int coord_mode) { return coord_mode == RPOOL_COORD_CHAINER ? 2 : 1; }
@@ -80,8 +93,10 @@ Workspace ws_split(void *ws, int R, int n_heads, int coord_mode)
     w.levels = static_cast<int *>(ws);
     w.order = w.levels + r;
     w.keys = w.order + r;
-    w.gstart = w.keys + r;
-    w.rects = w.gstart + kGstartInts;
+    w.rflags = w.keys + r;
+    w.gstart = w.rflags + r;
+    w.bh = w.gstart + kGstartInts;
+    w.rects = w.bh + ws_key_blocks(R) * kPlanMaxKeys;
     w.woff = reinterpret_cast<unsigned long long *>(w.rects + 4 * r);
     w.sizes = w.woff + r;
     w.det_total = w.sizes + r;
@@ -94,6 +109,38 @@ Workspace ws_split(void *ws, int R, int n_heads, int coord_mode)
 Workspace ws_split(void *ws, const rpool_problem *p)
 {
     return ws_split(ws, p->n_rois, p->n_heads, p->coord_mode);
+}
+
+// Validates rpool_problem.opt and fills in the defaults.
+int read_options(const rpool_problem *p, Options &o)
+{
+    const rpool_options &q = p->opt;
+    if (q.cta_threads != 0 && (q.cta_threads < 32 || q.cta_threads > kMaxThreads || q.cta_threads % 32))
+        return fail(RPOOL_ERR_INVALID, "opt.cta_threads=%d must be 0 or a multiple of 32 in [32,%d]",
+                    q.cta_threads, kMaxThreads);
+    if (q.schedule < 0 || q.schedule > RPOOL_SCHED_COARSE_FIRST)
+        return fail(RPOOL_ERR_INVALID, "opt.schedule=%d outside [0,3]", q.schedule);
+    if (q.force_path < 0 || q.force_path > RPOOL_PATH_TABLE)
+        return fail(RPOOL_ERR_INVALID, "opt.force_path=%d outside [0,2]", q.force_path);
+    if (q.fuse_heads_backward < 0 || q.fuse_heads_backward > 1)
+        return fail(RPOOL_ERR_INVALID, "opt.fuse_heads_backward=%d outside [0,1]", q.fuse_heads_backward);
+    if (q.prefetch_rows < -1 || q.prefetch_rows > 16)
+        return fail(RPOOL_ERR_INVALID, "opt.prefetch_rows=%d outside [-1,16]", q.prefetch_rows);
+    if (q.prefetch_rois < 0 || q.prefetch_rois > 65536)
+        return fail(RPOOL_ERR_INVALID, "opt.prefetch_rois=%d outside [0,65536]", q.prefetch_rois);
+    if (q.variant_forward < 0 || q.variant_forward > 2 || q.variant_backward < 0 || q.variant_backward > 2)
+        return fail(RPOOL_ERR_INVALID, "opt.variant_forward/backward outside [0,2]");
+    o.threads = q.cta_threads ? q.cta_threads : kDefaultThreads;
+    o.order = q.schedule;
+    o.force_path = q.force_path;
+    o.split_heads = q.fuse_heads_backward ? 0 : 1;
+    // kernel encoding: -1 off; -1-k row-ahead by k window rows; n >= 0 the whole RoI n slots later
+    if (q.prefetch_rois > 0) o.prefetch = q.prefetch_rois - 1;
+    else if (q.prefetch_rows < 0) o.prefetch = -1;
+    else o.prefetch = -1 - (q.prefetch_rows ? q.prefetch_rows : kDefaultPrefetchRows);
+    o.var_fwd = q.variant_forward ? q.variant_forward : RPOOL_DEFAULT_VARIANT_FWD;
+    o.var_bwd = q.variant_backward ? q.variant_backward : RPOOL_DEFAULT_VARIANT_BWD;
+    return RPOOL_OK;
 }
 
 int validate(const rpool_problem *p, void *ws, size_t ws_size, bool need_pooled)
@@ -152,7 +199,7 @@ int validate(const rpool_problem *p, void *ws, size_t ws_size, bool need_pooled)
 
 // Fills the kernel parameter block; returns the dynamic shared memory the
 // launch needs (control block + per-warp strips [+ transposed tables]).
-int fill_params(const rpool_problem *p, const Workspace &w, bool bwd, int threads, KParams &k)
+int fill_params(const rpool_problem *p, const Workspace &w, const Options &o, bool bwd, int threads, KParams &k)
 {
     memset(&k, 0, sizeof(k));
     for (int l = 0; l < p->n_levels; ++l) {
@@ -181,11 +228,11 @@ int fill_params(const rpool_problem *p, const Workspace &w, bool bwd, int thread
     }
     k.S = p->sampling_ratio;
     k.mode = p->coord_mode;
-    k.force_path = g_force_path.load();
+    k.force_path = o.force_path;
     const int ctl = (rec_bytes(p->n_heads) + 127) & ~127;
     const int warps = threads / 32;
-    k.prefetch = g_prefetch.load();
-    k.reverse = (bwd && g_order.load() == 1) ? 1 : 0;
+    k.prefetch = o.prefetch;
+    k.reverse = (bwd && o.order == RPOOL_SCHED_DEFAULT) ? 1 : 0;
     k.det = 0;
     k.det_rects = w.rects;
     k.det_woff = w.woff;
@@ -230,44 +277,7 @@ const char *rpool_last_error(void) { return g_err; }
 
 uint64_t rpool_launch_count(void) { return g_launches.load(); }
 
-int rpool_set_tuning(const char *key, int value)
-{
-    if (!key) return fail(RPOOL_ERR_INVALID, "key is NULL");
-    if (!strcmp(key, "prefetch")) {
-        if (value < -17 || value > 65536)
-            return fail(RPOOL_ERR_INVALID, "prefetch=%d outside [-17,65536]", value);
-        g_prefetch = value;
-    } else if (!strcmp(key, "threads")) {
-        if (value < 32 || value > kMaxThreads || value % 32)
-            return fail(RPOOL_ERR_INVALID, "threads=%d must be a multiple of 32 in [32,%d]", value,
-                        kMaxThreads);
-        g_threads = value;
-    } else if (!strcmp(key, "order")) {
-        if (value < 0 || value > 3) return fail(RPOOL_ERR_INVALID, "order=%d outside [0,3]", value);
-        g_order = value;
-    } else if (!strcmp(key, "force_path")) {
-        if (value < 0 || value > 2) return fail(RPOOL_ERR_INVALID, "force_path=%d outside [0,2]", value);
-        g_force_path = value;
-    } else if (!strcmp(key, "split_heads")) {
-        if (value < 0 || value > 1) return fail(RPOOL_ERR_INVALID, "split_heads=%d outside [0,1]", value);
-        g_split_heads = value;
-    } else {
-        return fail(RPOOL_ERR_INVALID, "unknown tuning key '%s'", key);
-    }
-    return RPOOL_OK;
-}
-
-int rpool_get_tuning(const char *key, int *value)
-{
-    if (!key || !value) return fail(RPOOL_ERR_INVALID, "NULL argument");
-    if (!strcmp(key, "prefetch")) *value = g_prefetch;
-    else if (!strcmp(key, "threads")) *value = g_threads;
-    else if (!strcmp(key, "order")) *value = g_order;
-    else if (!strcmp(key, "force_path")) *value = g_force_path;
-    else if (!strcmp(key, "split_heads")) *value = g_split_heads;
-    else return fail(RPOOL_ERR_INVALID, "unknown tuning key '%s'", key);
-    return RPOOL_OK;
-}
+const char *rpool_build_id(void) { return RPOOL_BUILD_ID; }
 
 int rpool_level_thresholds(float s0, float lvl0, float eps, int k_min, int k_max, float *out)
 {
@@ -336,7 +346,11 @@ int rpool_plan(const rpool_problem *p, void *ws, size_t ws_size, void *stream)
 {
     int rc = validate(p, ws, ws_size, false);
     if (rc) return rc;
+    Options o;
+    rc = read_options(p, o);
+    if (rc) return rc;
     if (p->n_rois == 0) return RPOOL_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Workspace w = ws_split(ws, p);
     PlanParams k;
     memset(&k, 0, sizeof(k));
@@ -350,22 +364,26 @@ int rpool_plan(const rpool_problem *p, void *ws, size_t ws_size, void *stream)
     int nimg = 1;
     for (int l = 0; l < p->n_levels; ++l) nimg = p->level[l].n_images > nimg ? p->level[l].n_images : nimg;
     k.n_images = nimg;
-    k.order_mode = g_order.load();
-    k.levels = w.levels; k.order = w.order; k.keys = w.keys; k.gstart = w.gstart;
-    rpool_plan_kernel<<<1, kPlanThreads, 0, static_cast<cudaStream_t>(stream)>>>(k);
-    CUDA_TRY(cudaGetLastError(), "rpool_plan_kernel launch");
-    g_launches++;
-    // every RoI's footprint tables and chunking, built once here (all RoIs in
-    // parallel) instead of in the prologue of every pooling CTA
-    for (int bwd = 0; bwd < rec_sets(p->coord_mode); ++bwd) {
-        KParams kp;
-        fill_params(p, w, bwd != 0, kTablesThreads, kp);
-        kp.reverse = 0;
-        rpool_tables_kernel<<<p->n_rois, kTablesThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-            kp, bwd, bwd ? w.recs_bwd : w.recs_fwd);
-        CUDA_TRY(cudaGetLastError(), "rpool_tables_kernel launch");
+    k.order_mode = o.order;
+    k.by_image = ((long long)nimg * p->n_levels <= kPlanMaxKeys) ? 1 : 0;
+    k.K = k.by_image ? nimg * p->n_levels : p->n_levels;
+    k.levels = w.levels; k.order = w.order; k.keys = w.keys; k.bh = w.bh; k.gstart = w.gstart;
+    k.rflags = w.rflags;
+    k.det_err = w.det_err;
+    // R <= kKeyBlock: one launch (every plan CTA ranks its RoI against all the others itself);
+    // larger sets get their keys and per-block histograms from rpool_keys_kernel first
+    k.n_blocks = 0;
+    if (p->n_rois > kKeyBlock && o.order != RPOOL_SCHED_INPUT) {
+        k.n_blocks = (int)ws_key_blocks(p->n_rois);
+        rpool_keys_kernel<<<k.n_blocks, kKeyBlock, 0, st>>>(k);
+        CUDA_TRY(cudaGetLastError(), "rpool_keys_kernel launch");
         g_launches++;
     }
+    KParams kp;
+    fill_params(p, w, o, false, kPlanThreads, kp);
+    rpool_plan_kernel<<<p->n_rois, kPlanThreads, 0, st>>>(kp, k, w.recs_fwd, w.recs_bwd);
+    CUDA_TRY(cudaGetLastError(), "rpool_plan_kernel launch");
+    g_launches++;
     return RPOOL_OK;
 }
 
@@ -373,13 +391,17 @@ int rpool_forward(const rpool_problem *p, void *ws, size_t ws_size, void *stream
 {
     int rc = validate(p, ws, ws_size, true);
     if (rc) return rc;
+    Options o;
+    rc = read_options(p, o);
+    if (rc) return rc;
     if (p->n_rois == 0) return RPOOL_OK;
     KParams k;
-    const int threads = g_threads.load();
-    const int smem = fill_params(p, ws_split(ws, p), false, threads, k);
+    const int threads = o.threads;
+    const int smem = fill_params(p, ws_split(ws, p), o, false, threads, k);
     if (smem > kMaxSmem)
         return fail(RPOOL_ERR_UNSUPPORTED, "forward needs %d bytes of shared memory; the limit is %d",
                     smem, kMaxSmem);
+    k.variant = o.var_fwd;
     rc = set_smem(rpool_forward_kernel, 0, smem);
     if (rc) return rc;
     rpool_forward_kernel<<<p->n_rois, threads, smem, static_cast<cudaStream_t>(stream)>>>(k);
@@ -390,10 +412,12 @@ int rpool_forward(const rpool_problem *p, void *ws, size_t ws_size, void *stream
 
 // Launches the two prepass kernels of the deterministic backward (window
 // rectangles, offsets of the private windows).
-static int det_prepass(const rpool_problem *p, void *ws, cudaStream_t st, KParams &k, int &threads)
+static int det_prepass(const rpool_problem *p, void *ws, const Options &o, cudaStream_t st, KParams &k,
+                       int &threads)
 {
-    if (g_order.load() != 1)
-        return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward needs the (image, level) schedule (order=1)");
+    if (o.order != RPOOL_SCHED_DEFAULT)
+        return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward needs the (image, level) schedule "
+                    "(opt.schedule = RPOOL_SCHED_DEFAULT)");
     if (p->feat_layout != RPOOL_NHWC || p->pool_layout != RPOOL_NHWC || (p->channels & 3) || p->channels > 128 * kGatherSlabs)
         return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward needs channels-last tensors with "
                     "C %% 4 == 0 and C <= %d", 128 * kGatherSlabs);
@@ -403,8 +427,8 @@ static int det_prepass(const rpool_problem *p, void *ws, cudaStream_t st, KParam
         return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward: images x levels = %d exceeds %d",
                     nimg * p->n_levels, kPlanMaxKeys);
     const Workspace w = ws_split(ws, p);
-    threads = g_threads.load();
-    fill_params(p, w, true, threads, k);
+    threads = o.threads;
+    fill_params(p, w, o, true, threads, k);
     k.reverse = 0;
     CUDA_TRY(cudaMemsetAsync(w.det_err, 0, sizeof(int), st), "cudaMemsetAsync(det_err)");
     if (p->n_rois > 0) {
@@ -424,11 +448,14 @@ int rpool_backward_det_bytes(const rpool_problem *p, void *ws, size_t ws_size, v
 {
     int rc = validate(p, ws, ws_size, true);
     if (rc) return rc;
+    Options o;
+    rc = read_options(p, o);
+    if (rc) return rc;
     if (!bytes_out) return fail(RPOOL_ERR_INVALID, "bytes_out is NULL");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     KParams k;
     int threads;
-    rc = det_prepass(p, ws, st, k, threads);
+    rc = det_prepass(p, ws, o, st, k, threads);
     if (rc) return rc;
     const Workspace w = ws_split(ws, p);
     unsigned long long total = 0;
@@ -438,19 +465,26 @@ int rpool_backward_det_bytes(const rpool_problem *p, void *ws, size_t ws_size, v
     return RPOOL_OK;
 }
 
-int rpool_det_status(void *ws, int32_t n_rois, void *stream, int32_t *err_out)
+int rpool_status_flags(const void *ws, int32_t n_rois, void *stream, int32_t *flags_out)
 {
-    if (!ws || !err_out || n_rois < 0) return fail(RPOOL_ERR_INVALID, "bad arguments");
-    const Workspace w = ws_split(ws, n_rois, 1, RPOOL_COORD_CAFFE2);   // fixed part only
+    if (!ws || !flags_out || n_rois < 0) return fail(RPOOL_ERR_INVALID, "bad arguments");
+    const Workspace w = ws_split(const_cast<void *>(ws), n_rois, 1, RPOOL_COORD_CAFFE2);   // fixed part only
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int e = 0;
-    CUDA_TRY(cudaMemcpyAsync(&e, w.det_err, sizeof(int), cudaMemcpyDeviceToHost, st), "copy det_err");
-    CUDA_TRY(cudaStreamSynchronize(st), "cudaStreamSynchronize");
-    *err_out = e;
+    int flags = 0;
+    if (n_rois > 0) {
+        // the per-RoI flags of the plan and the deterministic pass's flag are folded on the
+        // device into det_err's neighbour word, then one 8-byte copy
+        rpool_flags_kernel<<<1, 256, 0, st>>>(w.rflags, n_rois, w.det_err, w.det_err + 1);
+        CUDA_TRY(cudaGetLastError(), "rpool_flags_kernel launch");
+        g_launches++;
+        CUDA_TRY(cudaMemcpyAsync(&flags, w.det_err + 1, sizeof(int), cudaMemcpyDeviceToHost, st), "copy flags");
+        CUDA_TRY(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    }
+    *flags_out = flags;
     return RPOOL_OK;
 }
 
-static int backward_det(const rpool_problem *p, void *ws, cudaStream_t st)
+static int backward_det(const rpool_problem *p, void *ws, const Options &o, cudaStream_t st)
 {
     if (!p->det_workspace) return fail(RPOOL_ERR_WORKSPACE, "deterministic backward: det_workspace is NULL "
                                        "(size it with rpool_backward_det_bytes)");
@@ -458,20 +492,18 @@ static int backward_det(const rpool_problem *p, void *ws, cudaStream_t st)
         return fail(RPOOL_ERR_INVALID, "det_workspace must be 16-byte aligned");
     KParams k;
     int threads;
-    int rc = det_prepass(p, ws, st, k, threads);
+    int rc = det_prepass(p, ws, o, st, k, threads);
     if (rc) return rc;
     const Workspace w = ws_split(ws, p);
-    k.det = 1;
-    k.det_scratch = static_cast<float *>(p->det_workspace);
-    k.det_scratch_floats = p->det_workspace_bytes / sizeof(float);
     if (p->n_rois > 0) {
-        int smem = fill_params(p, w, true, threads, k);
+        int smem = fill_params(p, w, o, true, threads, k);
         while (smem > kMaxSmem && threads > 32) {
             threads -= 32;
-            smem = fill_params(p, w, true, threads, k);
+            smem = fill_params(p, w, o, true, threads, k);
         }
         k.reverse = 0;
         k.det = 1;
+        k.variant = kVariantRows;
         k.det_scratch = static_cast<float *>(p->det_workspace);
         k.det_scratch_floats = p->det_workspace_bytes / sizeof(float);
         rc = set_smem(rpool_backward_kernel, 1, smem);
@@ -509,38 +541,69 @@ static int backward_det(const rpool_problem *p, void *ws, cudaStream_t st)
     return RPOOL_OK;
 }
 
+// validation of the fields rpool_zero_fill reads
+static int validate_levels(const rpool_problem *p)
+{
+    if (!p) return fail(RPOOL_ERR_INVALID, "problem is NULL");
+    if (p->n_levels < 1 || p->n_levels > RPOOL_MAX_LEVELS)
+        return fail(RPOOL_ERR_INVALID, "n_levels=%d outside [1,%d]", p->n_levels, RPOOL_MAX_LEVELS);
+    if (p->channels < 1) return fail(RPOOL_ERR_INVALID, "channels=%d", p->channels);
+    for (int l = 0; l < p->n_levels; ++l) {
+        const rpool_level &L = p->level[l];
+        if (!L.data || L.n_images < 1 || L.height < 1 || L.width < 1)
+            return fail(RPOOL_ERR_INVALID, "level %d: data=%p n=%d h=%d w=%d", l, L.data,
+                        L.n_images, L.height, L.width);
+    }
+    return RPOOL_OK;
+}
+
+static int launch_zero(const rpool_problem *p, cudaStream_t st)
+{
+    ZeroParams z;
+    memset(&z, 0, sizeof(z));
+    z.n = p->n_levels;
+    for (int l = 0; l < p->n_levels; ++l) {
+        const unsigned long long n = (unsigned long long)p->level[l].n_images *
+                                     p->level[l].height * p->level[l].width * p->channels;
+        z.ptr[l] = static_cast<float *>(p->level[l].data);
+        if (reinterpret_cast<uintptr_t>(z.ptr[l]) & 15) { z.n4[l] = 0; z.tail[l] = n; }
+        else { z.n4[l] = n / 4; z.tail[l] = n % 4; }
+        if (z.tail[l] > 1024ull * 148 * 8)
+            return fail(RPOOL_ERR_UNSUPPORTED, "level %d gradient is not 16-byte aligned", l);
+    }
+    rpool_zero_kernel<<<148 * 8, 1024, 0, st>>>(z);
+    CUDA_TRY(cudaGetLastError(), "rpool_zero_kernel launch");
+    g_launches++;
+    return RPOOL_OK;
+}
+
+int rpool_zero_fill(const rpool_problem *p, void *stream)
+{
+    int rc = validate_levels(p);
+    if (rc) return rc;
+    return launch_zero(p, static_cast<cudaStream_t>(stream));
+}
+
 int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *stream)
 {
     int rc = validate(p, ws, ws_size, true);
     if (rc) return rc;
+    Options o;
+    rc = read_options(p, o);
+    if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (p->deterministic) return backward_det(p, ws, st);
+    if (p->deterministic) return backward_det(p, ws, o, st);
     if (!p->accumulate) {
-        ZeroParams z;
-        memset(&z, 0, sizeof(z));
-        z.n = p->n_levels;
-        unsigned long long most = 0;
-        for (int l = 0; l < p->n_levels; ++l) {
-            const unsigned long long n = (unsigned long long)p->level[l].n_images *
-                                         p->level[l].height * p->level[l].width * p->channels;
-            z.ptr[l] = static_cast<float *>(p->level[l].data);
-            if (reinterpret_cast<uintptr_t>(z.ptr[l]) & 15) { z.n4[l] = 0; z.tail[l] = n; }
-            else { z.n4[l] = n / 4; z.tail[l] = n % 4; }
-            most = z.n4[l] > most ? z.n4[l] : most;
-            if (z.tail[l] > 1024ull * 148 * 8)
-                return fail(RPOOL_ERR_UNSUPPORTED, "level %d gradient is not 16-byte aligned", l);
-        }
-        rpool_zero_kernel<<<148 * 8, 1024, 0, st>>>(z);
-        CUDA_TRY(cudaGetLastError(), "rpool_zero_kernel launch");
-        g_launches++;
+        rc = launch_zero(p, st);
+        if (rc) return rc;
     }
     if (p->n_rois == 0) return RPOOL_OK;
     const Workspace w = ws_split(ws, p);
     // Two pooled sizes: the backward pass has nothing to share between them (each reads its
     // own gy; the reductions into the gradient are per size either way), and one launch per
     // size keeps the per-CTA strips small (more L1 for the gy re-reads): 2 launches unless
-    // "split_heads" is 0.
-    const int parts = (p->n_heads > 1 && g_split_heads.load()) ? p->n_heads : 1;
+    // opt.fuse_heads_backward is set.
+    const int parts = (p->n_heads > 1 && o.split_heads) ? p->n_heads : 1;
     for (int part = 0; part < parts; ++part) {
         rpool_problem q = *p;
         if (parts > 1) {
@@ -550,13 +613,15 @@ int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *strea
             q.pooled[0] = p->pooled[part];
         }
         KParams k;
-        int threads = g_threads.load();
-        int smem = fill_params(&q, w, true, threads, k);
+        int threads = o.threads;
+        int smem = fill_params(&q, w, o, true, threads, k);
         while (smem > kMaxSmem && threads > 32) {  // two wide heads: fewer warps, same result
             threads -= 32;
-            smem = fill_params(&q, w, true, threads, k);
+            smem = fill_params(&q, w, o, true, threads, k);
         }
         k.rec_head = parts > 1 ? part : 0;
+        k.rec_stride = w.rec_stride;       // records keep the layout of the plan's head count
+        k.variant = o.var_bwd;
         rc = set_smem(rpool_backward_kernel, 1, smem);
         if (rc) return rc;
         rpool_backward_kernel<<<p->n_rois, threads, smem, st>>>(k);

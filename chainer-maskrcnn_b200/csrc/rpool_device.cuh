@@ -65,6 +65,7 @@ struct KParams {
     int rec_stride;
     int rec_head;    // first head part of the stored record this launch uses (0 unless heads are split)
     int force_path;
+    int variant;     // kernel variant of this launch (1 = rows, 2 = stream)
 };
 
 // ---------------------------------------------------------------------------
@@ -288,16 +289,6 @@ __device__ __forceinline__ void sts128(uint32_t a, float4 v)
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-__device__ __forceinline__ float lds32(uint32_t a)
-{
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts32(uint32_t a, float v)
-{
-    asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory");
-}
 // streaming (evict-first) global accesses for data touched exactly once
 #ifndef RPOOL_ST_POLICY
 #define RPOOL_ST_POLICY ".cs"
@@ -309,12 +300,6 @@ __device__ __forceinline__ void stg_stream128(float *p, float4 v)
 #endif
     asm volatile("st.global" RPOOL_ST_POLICY ".v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ float ldg_stream32(const float *p)
-{
-    float v;
-    asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
 }
 __device__ __forceinline__ float4 ldg_nc128(const float *p)
 {
@@ -348,51 +333,10 @@ __device__ __forceinline__ void stg128(float *p, float4 v)
     asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-__device__ __forceinline__ void red_add_f32(float *p, float v)
-{
-    asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
-}
-
 // bulk L2 prefetch through the TMA unit (bytes: multiple of 16)
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
-}
-
-// mbarrier + bulk async copy (the non-tensor TMA path: UBLKCP in SASS)
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_mbar_init()
-{
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    const uint32_t a = smem_u32(bar);
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" :: "r"(a), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, unsigned bytes,
-                                         unsigned long long *bar)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 }  // namespace rpool

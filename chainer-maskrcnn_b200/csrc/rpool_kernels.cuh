@@ -40,6 +40,15 @@ __device__ __forceinline__ AxisGeom axis_of(const KParams &P, const RoiCtx &c, b
                 : make_axis(P.mode, bwd, c.box.y1, c.box.y2, c.L.scale, P.PH[h], P.S, c.L.H);
 }
 
+// Layouts, channel count, pooled sizes and map width admit the table paths.
+__device__ __forceinline__ bool shapes_allow_tables(const KParams &P, const LevelDev &L)
+{
+    bool ok = (P.feat_layout == RPOOL_NHWC) && (P.pool_layout == RPOOL_NHWC) && (P.C % 4 == 0);
+    for (int h = 0; h < P.n_heads; ++h) ok = ok && P.PH[h] <= kPMax && P.PW[h] <= kPMax;
+    // the table path reads spans of kSW columns: the map must be that wide
+    return ok && L.W >= kSW;
+}
+
 __device__ __forceinline__ void roi_decode(const KParams &P, int slot, RoiCtx &c)
 {
     c.r = P.order[slot];
@@ -51,10 +60,7 @@ __device__ __forceinline__ void roi_decode(const KParams &P, int slot, RoiCtx &c
     c.b = q.b;
     c.box = q;
     c.valid = (q.b >= 0 && q.b < c.L.n_images);
-    bool ok = (P.feat_layout == RPOOL_NHWC) && (P.pool_layout == RPOOL_NHWC) && (P.C % 4 == 0);
-    for (int h = 0; h < P.n_heads; ++h) ok = ok && P.PH[h] <= kPMax && P.PW[h] <= kPMax;
-    // the table path reads spans of kSW columns: the map must be that wide
-    c.fast_ok = ok && c.L.W >= kSW;
+    c.fast_ok = shapes_allow_tables(P, c.L);
 }
 
 __device__ __forceinline__ int launch_slot(const KParams &P)
@@ -444,32 +450,6 @@ __device__ __forceinline__ void build_chunks(const KParams &P, const RoiCtx &c, 
     __syncthreads();
 }
 
-// Builds every RoI's record (footprint tables + chunking) for one direction:
-// one small CTA per schedule slot, all RoIs in parallel, once per plan.
-constexpr int kTablesThreads = 64;
-__global__ void __launch_bounds__(kTablesThreads)
-rpool_tables_kernel(const __grid_constant__ KParams P, int bwd, unsigned char *recs)
-{
-    __shared__ __align__(16) BlockCtl ctl_s;
-    BlockCtl *ctl = &ctl_s;
-    RoiCtx c;
-    roi_decode(P, blockIdx.x, c);
-    if (threadIdx.x == 0) {
-        ctl->r = c.r; ctl->lvl = c.lvl; ctl->b = c.b;
-        ctl->flags = (c.valid ? kRecValid : 0) | (c.fast_ok ? kRecShape : 0) | kRecFits;
-    }
-    if (c.valid && c.fast_ok) {      // (uniform) otherwise the consumer takes the generic path
-        build_tables(P, c, bwd != 0, ctl);
-        if (ctl->flags & kRecFits) build_chunks(P, c, ctl, kPMax);   // (uniform: read after the sync)
-    } else {
-        __syncthreads();
-    }
-    const uint4 *src = reinterpret_cast<const uint4 *>(ctl);
-    uint4 *dst = reinterpret_cast<uint4 *>(recs + (size_t)blockIdx.x * P.rec_stride);
-    const int n16 = rec_bytes(P.n_heads) >> 4;
-    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
-}
-
 __device__ __forceinline__ void ctx_from_record(const KParams &P, const BlockCtl *ctl, RoiCtx &c)
 {
     c.r = ctl->r; c.lvl = ctl->lvl; c.b = ctl->b;
@@ -808,8 +788,20 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
 }
 
 // ---------------------------------------------------------------------------
-// plan: level assignment + stable (image, level) binning
+// plan: level assignment + stable (image, level) binning + every RoI's record
 // ---------------------------------------------------------------------------
+// One 64-thread CTA per input RoI i (all RoIs in parallel, one wave for the sizes of
+// BASELINE.json).  The CTA finds its RoI's slot in the launch schedule -- the stable
+// rank of (key_i, i) among all RoIs, key = (image, level) in the order the schedule
+// asks for -- and writes the RoI's record (footprint tables + chunking, for the
+// forward geometry and, in RPOOL_COORD_CHAINER mode, a second one for the backward
+// geometry) at that slot.  There is no single-CTA sort on the critical path:
+//   R <= kKeyBlock   one launch: every CTA derives the keys of all RoIs itself
+//                    (R / 64 RoIs per thread, 20 bytes each, L1/L2 hits);
+//   R  > kKeyBlock   rpool_keys_kernel first writes the keys and one histogram per
+//                    block of kKeyBlock RoIs; a plan CTA then sums the histogram
+//                    entries that precede (key_i, block_i) and ranks its RoI inside
+//                    its own block.
 struct PlanParams {
     const float *rois;
     int R;
@@ -821,11 +813,17 @@ struct PlanParams {
     int k_min;
     int n_levels;
     int n_images;   // max over levels
-    int order_mode; // 0 identity, 1 (image, level asc), 2 (image, level desc), 3 (level desc, image)
-    int *levels;    // out
-    int *order;     // out
-    int *keys;      // scratch
-    int *gstart;    // out: first schedule slot of every (image, level) key, [n_keys] = R
+    int order_mode; // rpool_schedule
+    int K;          // number of keys
+    int by_image;   // keys include the image index (n_images * n_levels <= kPlanMaxKeys)
+    int n_blocks;   // key blocks (0: single launch)
+    int *levels;    // out: level of every RoI
+    int *order;     // out: schedule slot -> RoI
+    int *keys;      // out (two-launch mode): key of every RoI
+    int *bh;        // out (two-launch mode): [n_blocks][K] histograms
+    int *gstart;    // out: first schedule slot of every (image, level) key, [K..] = R
+    int *rflags;    // out: RPOOL_FLAG_* of every RoI
+    int *det_err;   // cleared here; raised by the deterministic backward
 };
 
 __device__ __forceinline__ int level_from_area(float y1, float x1, float y2, float x2,
@@ -840,80 +838,163 @@ __device__ __forceinline__ int level_from_area(float y1, float x1, float y2, flo
     return k;
 }
 
-constexpr int kPlanThreads = 1024;
+constexpr int kPlanThreads = 64;
 constexpr int kPlanMaxKeys = 256;
+constexpr int kKeyBlock = 1024;
+
+// Level (clipped to the pyramid, maskrcnn.py:141), schedule key and flags of RoI i.
+__device__ __forceinline__ int plan_key(const PlanParams &p, int i, int &lvl_out, int &flags_out)
+{
+    const RoiBox q = load_roi(p.rois, i, p.roi_format);
+    const int L = p.n_levels;
+    int lvl;
+    if (p.given_levels) lvl = __ldg(p.given_levels + i);
+    else if (p.given_levels_f32) lvl = (int)__ldg(p.given_levels_f32 + i);  // astype(int32)
+    else lvl = level_from_area(q.y1, q.x1, q.y2, q.x2, p.thr, p.n_thr, p.k_min);
+    int flags = 0;
+    if (lvl < 0 || lvl >= L) flags |= RPOOL_FLAG_LEVEL_CLIPPED;
+    lvl = lvl < 0 ? 0 : (lvl >= L ? L - 1 : lvl);
+    if (q.b < 0 || q.b >= p.n_images) flags |= RPOOL_FLAG_BAD_BATCH;
+    const int b = q.b < 0 ? 0 : (q.b >= p.n_images ? p.n_images - 1 : q.b);
+    const int lk = (p.order_mode >= RPOOL_SCHED_LEVEL_DESC) ? (L - 1 - lvl) : lvl;
+    lvl_out = lvl;
+    flags_out = flags;
+    // COARSE_FIRST: coarse levels (the widest windows, the longest CTAs) of every image first
+    return !p.by_image ? lk : (p.order_mode == RPOOL_SCHED_COARSE_FIRST ? lk * p.n_images + b : b * L + lk);
+}
+
+__global__ void __launch_bounds__(kKeyBlock)
+rpool_keys_kernel(const __grid_constant__ PlanParams p)
+{
+    __shared__ int hist[kPlanMaxKeys];
+    const int tid = threadIdx.x;
+    for (int k = tid; k < p.K; k += kKeyBlock) hist[k] = 0;
+    __syncthreads();
+    const int i = blockIdx.x * kKeyBlock + tid;
+    int key = -1 - (tid & 31);
+    if (i < p.R) {
+        int lvl, fl;
+        key = plan_key(p, i, lvl, fl);
+        p.keys[i] = key;
+    }
+    // one shared-memory atomic per distinct key and warp
+    const unsigned same = __match_any_sync(0xffffffffu, key);
+    if (i < p.R && (same & ((1u << (tid & 31)) - 1u)) == 0) atomicAdd(&hist[key], __popc(same));
+    __syncthreads();
+    for (int k = tid; k < p.K; k += kKeyBlock) p.bh[blockIdx.x * p.K + k] = hist[k];
+}
+
+__device__ __forceinline__ int plan_cta_sum(int v, int *scratch)
+{
+    // sum over the CTA's two warps
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return scratch[0] + scratch[1];
+}
 
 __global__ void __launch_bounds__(kPlanThreads)
-rpool_plan_kernel(const __grid_constant__ PlanParams p)
+rpool_plan_kernel(const __grid_constant__ KParams P, const __grid_constant__ PlanParams p,
+                  unsigned char *recs_fwd, unsigned char *recs_bwd)
 {
-    __shared__ int hist[32 * kPlanMaxKeys];
-    __shared__ int base[kPlanMaxKeys];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int L = p.n_levels;
-    int K = p.n_images * L;
-    const bool by_image = (K <= kPlanMaxKeys);
-    if (!by_image) K = L;
+    __shared__ __align__(16) BlockCtl ctl_s;
+    __shared__ int s_sum[2];
+    __shared__ int s_hist[kPlanMaxKeys + 1];
+    BlockCtl *ctl = &ctl_s;
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x;
+    const bool first = (i == 0);          // this CTA also writes gstart
 
-    for (int i = tid; i < p.R; i += kPlanThreads) {
-        const RoiBox q = load_roi(p.rois, i, p.roi_format);
-        int lvl;
-        if (p.given_levels) lvl = p.given_levels[i];
-        else if (p.given_levels_f32) lvl = (int)p.given_levels_f32[i];  // astype(int32)
-        else lvl = level_from_area(q.y1, q.x1, q.y2, q.x2, p.thr, p.n_thr, p.k_min);
-        lvl = lvl < 0 ? 0 : (lvl >= L ? L - 1 : lvl);  // maskrcnn.py:141
-        p.levels[i] = lvl;
-        int b = q.b < 0 ? 0 : (q.b >= p.n_images ? p.n_images - 1 : q.b);
-        const int lk = (p.order_mode >= 2) ? (L - 1 - lvl) : lvl;
-        // mode 3: coarse levels (the widest windows, the longest CTAs) of every image first
-        p.keys[i] = !by_image ? lk : (p.order_mode == 3 ? lk * p.n_images + b : b * L + lk);
-    }
-    if (p.order_mode == 0) {
-        for (int i = tid; i < p.R; i += kPlanThreads) p.order[i] = i;
-        if (p.gstart)
-            for (int k = tid; k < kPlanMaxKeys + 1; k += kPlanThreads) p.gstart[k] = -1;
-        return;
-    }
-    for (int i = tid; i < 32 * K; i += kPlanThreads) hist[i] = 0;
-    __syncthreads();
-    // warp w owns the contiguous chunk [w*chunk, (w+1)*chunk)
-    const int chunk = ((p.R + 31) / 32 + 31) / 32 * 32;
-    const int beg = warp * chunk;
-    const int end = beg + chunk < p.R ? beg + chunk : p.R;
-    for (int i = beg + lane; i < end; i += 32) atomicAdd(&hist[warp * K + p.keys[i]], 1);
-    __syncthreads();
-    if (tid < K) {
-        int run = 0;
-        for (int w = 0; w < 32; ++w) {
-            const int t = hist[w * K + tid];
-            hist[w * K + tid] = run;
-            run += t;
+    int lvl, fl;
+    const int key = plan_key(p, i, lvl, fl);
+    int slot = i;
+    if (first)
+        for (int k = tid; k <= kPlanMaxKeys; k += kPlanThreads) s_hist[k] = 0;
+    if (first) __syncthreads();
+    if (p.order_mode != RPOOL_SCHED_INPUT) {
+        int acc = 0;
+        if (p.n_blocks == 0) {
+            for (int j = tid; j < p.R; j += kPlanThreads) {
+                int l2, f2;
+                const int kj = plan_key(p, j, l2, f2);
+                acc += (kj < key || (kj == key && j < i)) ? 1 : 0;
+                if (first) atomicAdd(&s_hist[kj], 1);
+            }
+        } else {
+            const int blk = i / kKeyBlock;
+            const int n = p.n_blocks * p.K;
+            for (int e = tid; e < n; e += kPlanThreads) {
+                const int b = e / p.K, k = e - b * p.K;
+                const int v = __ldg(p.bh + e);
+                acc += (k < key || (k == key && b < blk)) ? v : 0;
+                if (first) atomicAdd(&s_hist[k], v);
+            }
+            for (int j = blk * kKeyBlock + tid; j < i; j += kPlanThreads)
+                acc += (__ldg(p.keys + j) == key) ? 1 : 0;
         }
-        base[tid] = run;
+        slot = plan_cta_sum(acc, s_sum);
     }
-    __syncthreads();
     if (tid == 0) {
-        int run = 0;
-        for (int k = 0; k < K; ++k) {
-            const int t = base[k];
-            base[k] = run;
-            run += t;
+        p.levels[i] = lvl;
+        p.order[slot] = i;
+        p.rflags[i] = fl;
+        if (first) *p.det_err = 0;
+    }
+    if (first && p.gstart) {
+        __syncthreads();
+        if (tid == 0) {
+            const bool groups = p.by_image && p.order_mode == RPOOL_SCHED_DEFAULT;
+            int run = 0;
+            for (int k = 0; k <= kPlanMaxKeys; ++k) {
+                const int t = s_hist[k];
+                p.gstart[k] = groups ? (k < p.K ? run : p.R) : -1;
+                run += t;
+            }
         }
     }
-    __syncthreads();
-    if (p.gstart) {
-        for (int k = tid; k < kPlanMaxKeys + 1; k += kPlanThreads)
-            p.gstart[k] = (by_image && p.order_mode == 1) ? (k < K ? base[k] : p.R) : -1;
+
+    // ---- the RoI's record(s)
+    RoiCtx c;
+    c.r = i;
+    c.lvl = lvl;
+    c.L = P.lvl[lvl];
+    c.box = load_roi(P.rois, i, P.roi_format);
+    c.b = c.box.b;
+    c.valid = (c.b >= 0 && c.b < c.L.n_images);
+    c.fast_ok = shapes_allow_tables(P, c.L);
+    const int n16 = rec_bytes(P.n_heads) >> 4;
+    for (int bwd = 0; bwd < (recs_bwd != recs_fwd ? 2 : 1); ++bwd) {
+        __syncthreads();    // the previous set has left shared memory
+        if (tid == 0) {
+            ctl->r = c.r; ctl->lvl = c.lvl; ctl->b = c.b;
+            ctl->flags = (c.valid ? kRecValid : 0) | (c.fast_ok ? kRecShape : 0) | kRecFits;
+        }
+        if (c.valid && c.fast_ok) {      // (uniform) otherwise the consumer takes the generic path
+            build_tables(P, c, bwd != 0, ctl);
+            if (ctl->flags & kRecFits) build_chunks(P, c, ctl, kPMax);   // (uniform: read after the sync)
+        } else {
+            __syncthreads();
+        }
+        const uint4 *src = reinterpret_cast<const uint4 *>(ctl);
+        uint4 *dst = reinterpret_cast<uint4 *>((bwd ? recs_bwd : recs_fwd) + (size_t)slot * P.rec_stride);
+        for (int k = tid; k < n16; k += kPlanThreads) dst[k] = src[k];
     }
-    for (int i0 = beg; i0 < end; i0 += 32) {
-        const int i = i0 + lane;
-        const bool active = i < end;
-        const int key = active ? p.keys[i] : -1 - lane;
-        const unsigned mask = __match_any_sync(0xffffffffu, key);
-        const int rank = __popc(mask & ((1u << lane) - 1u));
-        if (active) p.order[base[key] + hist[warp * K + key] + rank] = i;
-        __syncwarp();
-        if (active && rank == 0) hist[warp * K + key] += __popc(mask);
-        __syncwarp();
+}
+
+// OR of the per-RoI plan flags and the deterministic pass's flag (rpool_status_flags)
+__global__ void rpool_flags_kernel(const int *__restrict__ rflags, int n, const int *det_err, int *out)
+{
+    __shared__ int acc;
+    if (threadIdx.x == 0) acc = 0;
+    __syncthreads();
+    int f = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) f |= rflags[i];
+    if (f) atomicOr(&acc, f);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int e = *det_err;
+        *out = acc | (e == 1 ? RPOOL_FLAG_DET_GENERIC : 0) | (e == 2 ? RPOOL_FLAG_DET_SCRATCH : 0);
     }
 }
 

@@ -38,12 +38,14 @@ class InvalidType(TypeError):
 class ROIAlign2D(object):
     """RoI align over a set of 2d planes."""
 
-    def __init__(self, outh, outw, spatial_scale, sampling_ratio=1):
+    def __init__(self, outh, outw, spatial_scale, sampling_ratio=1, options=None):
         self.outh, self.outw = outh, outw
         self.spatial_scale = spatial_scale
         self.sampling_ratio = sampling_ratio
+        self.options = options            # rpool_options fields by name (experiments)
         self._bottom_data_shape = None
         self._plan = None
+        self._plan_key = None
 
     # -- type checking ------------------------------------------------------
     def check_type_forward(self, in_types):
@@ -72,7 +74,8 @@ class ROIAlign2D(object):
         (top,), self._plan = _engine.forward(
             [bottom_data], bottom_rois, None, [self.spatial_scale],
             [(self.outh, self.outw)], sampling_ratio=self.sampling_ratio,
-            roi_format=_lib.ROI_XY)
+            roi_format=_lib.ROI_XY, options=self.options)
+        self._plan_key = _rois_key(bottom_rois)
         return top,
 
     def backward_gpu(self, inputs, gy):
@@ -80,7 +83,9 @@ class ROIAlign2D(object):
         # remembered input shape are needed; inputs[0] may be None.
         bottom_rois = inputs[1]
         plan = self._plan
-        if plan is None or plan.rois.data_ptr() != bottom_rois.data_ptr():
+        # the forward plan (per-RoI tables, schedule) is reused only for the very same RoI
+        # tensor, unmodified since: same storage, shape and torch version counter
+        if plan is None or self._plan_key != _rois_key(bottom_rois):
             plan = self._make_plan(bottom_rois)
         (bottom_diff,) = _engine.backward(plan, [gy[0]])
         return bottom_diff, None
@@ -90,7 +95,8 @@ class ROIAlign2D(object):
             raise RuntimeError("backward called before forward: input shape unknown")
         return _engine.make_plan([self._bottom_data_shape], bottom_rois, None,
                                  [self.spatial_scale], [(self.outh, self.outw)],
-                                 sampling_ratio=self.sampling_ratio, roi_format=_lib.ROI_XY)
+                                 sampling_ratio=self.sampling_ratio, roi_format=_lib.ROI_XY,
+                                 options=self.options)
 
     # -- host-array entry points (computed on the GPU) -----------------------
     def forward_cpu(self, inputs):
@@ -140,6 +146,10 @@ class ROIAlign2D(object):
                              out_sizes=[(self.outh, self.outw)],
                              sampling_ratio=self.sampling_ratio, roi_format=_lib.ROI_XY)
         return y
+
+
+def _rois_key(rois):
+    return (rois.data_ptr(), tuple(rois.shape), tuple(rois.stride()), rois._version, str(rois.device))
 
 
 def _np_dtype(a):

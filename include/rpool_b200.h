@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define RPOOL_VERSION 100          /* 0.1.0 */
+#define RPOOL_VERSION 200          /* 0.2.0 */
 #define RPOOL_MAX_LEVELS 8
 #define RPOOL_MAX_HEADS 2
 
@@ -78,6 +78,38 @@ typedef enum rpool_coord_mode {
      * samples beyond [-1, size] contribute zero; backward is its adjoint. */
     RPOOL_COORD_CAFFE2 = 1
 } rpool_coord_mode;
+
+/* Per-call options (all zero = defaults).  They live in the problem block: the
+ * library keeps no process-wide mutable state besides a per-device cache of the
+ * shared-memory attribute it has already raised. */
+typedef enum rpool_schedule {
+    RPOOL_SCHED_DEFAULT = 0,     /* RoIs binned by (image, level fine->coarse): L2 locality */
+    RPOOL_SCHED_INPUT = 1,       /* input order */
+    RPOOL_SCHED_LEVEL_DESC = 2,  /* (image, level coarse->fine) */
+    RPOOL_SCHED_COARSE_FIRST = 3 /* (level coarse->fine, image) */
+} rpool_schedule;
+
+typedef enum rpool_path {
+    RPOOL_PATH_AUTO = 0,
+    RPOOL_PATH_GENERIC = 1, /* tap by tap in the reference's operation order (any layout) */
+    RPOOL_PATH_TABLE = 2    /* vectorised channels-last path where the shapes allow it    */
+} rpool_path;
+
+typedef struct rpool_options {
+    int32_t cta_threads;    /* CTA size of the pooling kernels: 0 = 128; multiple of 32 in [32,256] */
+    int32_t schedule;       /* rpool_schedule */
+    int32_t force_path;     /* rpool_path */
+    int32_t fuse_heads_backward; /* 0: one backward launch per pooled size; 1: one launch for both */
+    int32_t prefetch_rows;  /* backward, rows variant: bulk L2 prefetch of the upstream gradient rows
+                             * the warp's task `prefetch_rows` window rows ahead is the first to need;
+                             * 0 = default (2), -1 = off, 1..16 */
+    int32_t prefetch_rois;  /* backward, rows variant: > 0 replaces the row-ahead prefetch by the whole
+                             * RoI of the CTA scheduled prefetch_rois - 1 slots later */
+    int32_t variant_forward;  /* 0 = default kernel; 1 = "rows" (one bin row per warp task);
+                               * 2 = "stream" (one chunk per warp task, window rows loaded once) */
+    int32_t variant_backward; /* 0 = default; 1 = "rows" (one window row per warp task);
+                               * 2 = "stream" (one chunk per warp task, gy rows loaded once) */
+} rpool_options;
 
 /* One pyramid level.  `data` is the feature map in rpool_forward (read) and
  * the dense feature gradient in rpool_backward (written). */
@@ -131,6 +163,8 @@ typedef struct rpool_problem {
      * rpool_backward_det_bytes (device memory, 16-byte aligned) */
     void *det_workspace;
     size_t det_workspace_bytes;
+
+    rpool_options opt;
 } rpool_problem;
 
 RPOOL_API int rpool_version(void);
@@ -139,16 +173,10 @@ RPOOL_API const char *rpool_last_error(void);
 /* Number of kernels this library has launched in the calling process. */
 RPOOL_API uint64_t rpool_launch_count(void);
 
-/* Tuning knobs for experiments ("prefetch", "threads", "order", "force_path", "split_heads").
- * "split_heads": 1 (default) runs the backward pass of a two-size problem as one launch
- * per pooled size (the sizes share nothing in that direction); 0 = one launch for both.
- * "prefetch" (backward, bulk L2 prefetch of the upstream gradient): -1 off; -1-k
- * (k = 1..16) row-ahead, the bin rows that window row i+k is the first to need are
- * requested while row i is processed (default -3, k = 2); n >= 0 the whole RoI of the
- * CTA scheduled n slots later.  Results do not depend on it.
- * Unknown keys return RPOOL_ERR_INVALID. */
-RPOOL_API int rpool_set_tuning(const char *key, int value);
-RPOOL_API int rpool_get_tuning(const char *key, int *value);
+/* Hash of the sources this library was compiled from ("unknown" when the build
+ * did not define RPOOL_BUILD_ID): bindings that have the sources at hand compare
+ * it with their own hash and refuse a stale binary. */
+RPOOL_API const char *rpool_build_id(void);
 
 /* Host helper: float32 area thresholds of floor(lvl0 + log2(sqrt(area)/s0 + eps))
  * for levels k_min+1..k_max, found by bisection with this libc's log2f.  The
@@ -197,6 +225,13 @@ RPOOL_API int rpool_forward(const rpool_problem *problem, void *workspace, size_
 RPOOL_API int rpool_backward(const rpool_problem *problem, void *workspace, size_t workspace_bytes,
                    void *stream);
 
+/* Zero fill of every level[l].data (N*H*W*C floats each) in one launch: what
+ * rpool_backward does first when accumulate == 0.  Exposed so that a caller can
+ * run it early on another stream (it depends on nothing) and then call
+ * rpool_backward with accumulate = 1 -- the step helper of the Python package
+ * overlaps it with rpool_plan / rpool_forward that way.  Needs no workspace. */
+RPOOL_API int rpool_zero_fill(const rpool_problem *problem, void *stream);
+
 /* Deterministic variant (problem->deterministic = 1): a segmented reduction.
  * Every RoI writes its window contribution to a private window in
  * det_workspace with plain stores, then every feature cell sums the windows that
@@ -204,11 +239,20 @@ RPOOL_API int rpool_backward(const rpool_problem *problem, void *workspace, size
  * fill): bit-identical from run to run.  The scratch size depends on the RoIs:
  * rpool_backward_det_bytes computes it on the device and SYNCHRONISES `stream`
  * to return it.  RoIs that would need the generic kernel path
- * cannot be ordered: they are skipped and flagged, query with rpool_det_status
- * (0 = clean; synchronises `stream`). */
+ * cannot be ordered: they are skipped and flagged (RPOOL_FLAG_DET_*). */
 RPOOL_API int rpool_backward_det_bytes(const rpool_problem *problem, void *workspace,
                                        size_t workspace_bytes, void *stream, size_t *bytes_out);
-RPOOL_API int rpool_det_status(void *workspace, int32_t n_rois, void *stream, int32_t *err_out);
+
+/* Sticky flags the kernels raise in the workspace (cleared by rpool_plan):
+ * what the reference reports with an exception (IndexError in the NumPy path,
+ * roi_align_2d.py:76-86) is computed safely here and flagged instead.
+ * rpool_status_flags copies them to the host and SYNCHRONISES `stream`. */
+#define RPOOL_FLAG_BAD_BATCH 1     /* a RoI's batch index is outside [0, n_images): zero rows, no gradient */
+#define RPOOL_FLAG_LEVEL_CLIPPED 2 /* a given level was outside the pyramid and was clipped (maskrcnn.py:141) */
+#define RPOOL_FLAG_DET_GENERIC 4   /* deterministic backward: a RoI needs the generic path and was skipped */
+#define RPOOL_FLAG_DET_SCRATCH 8   /* deterministic backward: det_workspace does not match the plan */
+RPOOL_API int rpool_status_flags(const void *workspace, int32_t n_rois, void *stream,
+                                 int32_t *flags_out);
 
 /* Read back the schedule of the last plan (for tests): device->host copies of
  * the per-RoI level and the permutation; synchronises `stream`. */

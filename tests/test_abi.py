@@ -23,7 +23,7 @@ def _declared_symbols():
 def test_library_is_in_tree_and_loads():
     L = _lib.lib()
     assert os.path.dirname(_lib._build.LIB_PATH) == os.path.join(ROOT, "chainer-maskrcnn_b200")
-    assert L.rpool_version() == 100
+    assert L.rpool_version() == 200 == _lib.VERSION
 
 
 def test_every_declared_symbol_is_exported():
@@ -54,15 +54,38 @@ def test_thresholds_libc_equal_numpy():
         assert np.array_equal(np.array(a, np.float32), np.array(b, np.float32))
 
 
-def test_tuning_roundtrip_and_errors():
-    old = _lib.get_tuning("prefetch")
-    _lib.set_tuning(prefetch=9)
-    assert _lib.get_tuning("prefetch") == 9
-    _lib.set_tuning(prefetch=old)
-    with pytest.raises(_lib.RpoolError):
-        _lib.set_tuning(threads=100)
-    with pytest.raises(_lib.RpoolError):
-        _lib.set_tuning(nonsense=1)
+def test_build_id_matches_the_sources():
+    """A stale binary is never loaded: the library carries the hash of the sources it was
+    compiled from, and the binding compares it with the tree's."""
+    assert _lib.build_id() == _lib._build.source_hash() != "unknown"
+    assert not _lib._build.is_stale()
+
+
+def test_binding_needs_nothing_but_the_standard_library():
+    """`import chainer_maskrcnn_b200._lib` must not pull torch or numpy: a CuPy/Chainer host
+    binds the C ABI through it."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import chainer_maskrcnn_b200._lib as L; "
+            "assert L.lib().rpool_version() == 200; "
+            "bad = [m for m in ('torch', 'numpy', 'cupy') if m in sys.modules]; assert not bad, bad" % ROOT)
+    subprocess.check_call([sys.executable, "-c", code])
+
+
+def test_options_validation():
+    L = _lib.lib()
+    raw = ctypes.create_string_buffer(65536 + 16)
+    ws = ctypes.c_void_p((ctypes.addressof(raw) + 15) & ~15)
+    for bad in (dict(cta_threads=100), dict(cta_threads=512), dict(schedule=4), dict(force_path=3),
+                dict(prefetch_rows=17), dict(prefetch_rois=-1), dict(variant_forward=3),
+                dict(variant_backward=-1), dict(fuse_heads_backward=2)):
+        p = _problem()
+        p.opt = _lib.make_options(**bad)
+        for fn in (L.rpool_plan, L.rpool_forward, L.rpool_backward):
+            assert fn(ctypes.byref(p), ws, 65536, None) == 1, bad
+            assert b"opt." in L.rpool_last_error()
+    with pytest.raises(ValueError):
+        _lib.make_options(nonsense=1)
 
 
 def _problem(**kw):
@@ -110,6 +133,10 @@ def test_workspace_errors_without_gpu():
     assert L.rpool_forward(ctypes.byref(p), ws, 16, None) == 3
     assert L.rpool_workspace_bytes(1000) >= 3 * 4 * 1000
     assert L.rpool_plan(None, ws, 16, None) == 1
+    assert L.rpool_zero_fill(None, None) == 1
+    q = _problem()
+    q.level[0].data = None
+    assert L.rpool_zero_fill(ctypes.byref(q), None) == 1
     # the deterministic variant needs its scratch (sized by rpool_backward_det_bytes)
     # and channels-last tensors
     p = _problem(deterministic=1)

@@ -25,13 +25,6 @@ BWD_TOL = 1e-4
 PATHS = {"auto": _lib.PATH_AUTO, "generic": _lib.PATH_GENERIC, "table": _lib.PATH_TABLE}
 
 
-@pytest.fixture(autouse=True)
-def _reset_tuning():
-    defaults = {k: _lib.get_tuning(k) for k in ("prefetch", "threads", "order", "force_path", "split_heads")}
-    yield
-    _lib.set_tuning(**defaults)
-
-
 def dev(a, channels_last=False):
     t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
     if channels_last and t.dim() == 4:
@@ -44,11 +37,11 @@ def host(t):
 
 
 def run_fused(feats, rois_yx, levels, scales, out_sizes, S=1, mode=None, channels_last=True,
-              gys=None, levels_dtype=np.int32, deterministic=False):
+              gys=None, levels_dtype=np.int32, deterministic=False, options=None):
     f = [dev(x, channels_last) for x in feats]
     lv = None if levels is None else dev(np.asarray(levels).astype(levels_dtype))
     outs, plan = _engine.forward(f, dev(rois_yx), lv, scales, out_sizes, sampling_ratio=S,
-                                 coord_mode=mode, roi_format=_lib.ROI_YX)
+                                 coord_mode=mode, roi_format=_lib.ROI_YX, options=options)
     for o in outs:
         assert o.is_contiguous(memory_format=torch.channels_last) or o.numel() == 0 or o.shape[1] == 1 \
             or o.shape[1] % 4 != 0        # (a channel count the shim padded: a view of the padded result)
@@ -94,8 +87,8 @@ def test_golden_reference_fixture_single_level_op(golden_dir):
     outh, outw, scale = int(d["outh"]), int(d["outw"]), float(d["scale"])
     x, rois, gy = dev(d["x"]), dev(d["rois"]), dev(d["gy"])
     for path in ("auto", "generic", "table"):
-        _lib.set_tuning(force_path=PATHS[path])
-        f = ROIAlign2D(outh, outw, scale)
+        opt = dict(force_path=PATHS[path])
+        f = ROIAlign2D(outh, outw, scale, options=opt)
         (y,) = f.forward_gpu((x, rois))
         assert y.dtype == torch.float32 and tuple(y.shape) == tuple(d["gy"].shape)
         assert oracle.rel_err(host(y), d["y"]) <= FWD_TOL, path
@@ -107,7 +100,7 @@ def test_golden_reference_fixture_single_level_op(golden_dir):
         assert oracle.rel_err(host(gx), d["gx"]) <= BWD_TOL, path
         for S in (1, 2, 3):
             (y2,), _ = _engine.forward([x], rois, None, [scale], [(outh, outw)], S,
-                                       _lib.COORD_CAFFE2, _lib.ROI_XY)
+                                       _lib.COORD_CAFFE2, _lib.ROI_XY, options=opt)
             assert oracle.rel_err(host(y2), d["y_caffe2_s%d" % S]) <= FWD_TOL, (path, S)
             if path == "generic":
                 assert np.array_equal(host(y2), d["y_caffe2_s%d" % S])
@@ -183,15 +176,18 @@ def test_levels_random_million_bit_exact():
 # ---------------------------------------------------------------------------
 # seeded random cases against the oracle, every kernel path
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("path,prefetch", [("auto", -3), ("generic", -1), ("table", 0), ("table", 7), ("table", -2), ("table", -1)])
+@pytest.mark.parametrize("path,prefetch", [("auto", {}), ("generic", dict(prefetch_rows=-1)),
+                                           ("table", dict(prefetch_rois=1)), ("table", dict(prefetch_rois=8)),
+                                           ("table", dict(prefetch_rows=1)), ("table", dict(prefetch_rows=-1))])
+@pytest.mark.parametrize("variant", [_lib.VARIANT_ROWS, _lib.VARIANT_STREAM])
 @pytest.mark.parametrize("mode_name,S", [("chainer", 1), ("caffe2", 1), ("caffe2", 2), ("caffe2", 3)])
-def test_fused_vs_oracle(path, prefetch, mode_name, S):
+def test_fused_vs_oracle(path, prefetch, variant, mode_name, S):
     rng, feats, rois, levels, scales = make_case(seed=S * 7 + len(path))
-    _lib.set_tuning(force_path=PATHS[path], prefetch=prefetch)
+    opt = dict(force_path=PATHS[path], variant_forward=variant, variant_backward=variant, **prefetch)
     mode = _lib.COORD_CHAINER if mode_name == "chainer" else _lib.COORD_CAFFE2
     sizes = [7, 14]
     gys = [synth.make_gy(rng, rois.shape[0], feats[0].shape[1], P) for P in sizes]
-    outs, grads, plan = run_fused(feats, rois, levels, scales, sizes, S, mode, gys=gys)
+    outs, grads, plan = run_fused(feats, rois, levels, scales, sizes, S, mode, gys=gys, options=opt)
     want, wgrads = oracle_fused(feats, rois, levels, scales, sizes, S, mode_name, gys)
     for o, w in zip(outs, want):
         assert oracle.rel_err(o, w) <= FWD_TOL
@@ -201,12 +197,14 @@ def test_fused_vs_oracle(path, prefetch, mode_name, S):
         assert oracle.rel_err(g, w) <= BWD_TOL
 
 
+@pytest.mark.parametrize("variant", [_lib.VARIANT_ROWS, _lib.VARIANT_STREAM])
 @pytest.mark.parametrize("threads", [32, 64, 224, 256])
-def test_block_sizes(threads):
+def test_block_sizes(threads, variant):
     rng, feats, rois, levels, scales = make_case(seed=3, C=128, per_img=60)
-    _lib.set_tuning(threads=threads)
     gys = [synth.make_gy(rng, rois.shape[0], 128, 14)]
-    outs, grads, _ = run_fused(feats, rois, levels, scales, [14], 2, gys=gys)
+    outs, grads, _ = run_fused(feats, rois, levels, scales, [14], 2, gys=gys,
+                               options=dict(cta_threads=threads, variant_forward=variant,
+                                            variant_backward=variant))
     want, wgrads = oracle_fused(feats, rois, levels, scales, [14], 2, "caffe2", gys)
     assert oracle.rel_err(outs[0], want[0]) <= FWD_TOL
     for g, w in zip(grads, wgrads):
@@ -216,12 +214,12 @@ def test_block_sizes(threads):
 @pytest.mark.parametrize("split", [0, 1])
 @pytest.mark.parametrize("mode_name,S", [("chainer", 1), ("caffe2", 2)])
 def test_two_pooled_sizes_backward_fused_or_one_launch_per_size(split, mode_name, S):
-    # "split_heads": one backward launch per pooled size (default) or one for both
-    _lib.set_tuning(split_heads=split)
+    # one backward launch per pooled size (default) or, opt.fuse_heads_backward, one for both
     rng, feats, rois, levels, scales = make_case(31, per_img=120)
     C = feats[0].shape[1]
     gys = [synth.make_gy(rng, rois.shape[0], C, 7), synth.make_gy(rng, rois.shape[0], C, 14)]
-    outs, grads, plan = run_fused(feats, rois, None, scales, [7, 14], S=S, gys=gys)
+    outs, grads, plan = run_fused(feats, rois, None, scales, [7, 14], S=S, gys=gys,
+                                  options=dict(fuse_heads_backward=1 - split))
     g_cl = [dev(g, True) for g in gys]
     n0 = _lib.launch_count()
     _engine.backward(plan, g_cl)
@@ -287,9 +285,8 @@ def test_large_pooled_size_and_adaptive_sampling():
             assert np.array_equal(outs[0], want[0]), (P, S)
         else:
             assert oracle.rel_err(outs[0], want[0]) <= FWD_TOL, (P, S)
-        _lib.set_tuning(force_path=_lib.PATH_GENERIC)
-        outs, _, _ = run_fused(feats, rois, levels, scales, [P], S, _lib.COORD_CAFFE2)
-        _lib.set_tuning(force_path=_lib.PATH_AUTO)
+        outs, _, _ = run_fused(feats, rois, levels, scales, [P], S, _lib.COORD_CAFFE2,
+                               options=dict(force_path=_lib.PATH_GENERIC))
         assert np.array_equal(outs[0], want[0]), (P, S, "generic")
     gy = synth.make_gy(rng, rois.shape[0], 8, 7)
     _, grads, _ = run_fused(feats, rois, levels, scales, [7], 0, _lib.COORD_CAFFE2, gys=[gy])
@@ -320,10 +317,10 @@ def test_edge_cases_caffe2_borders_and_degenerate():
                      [0, 25, 18, 80, 70]], np.float32)       # xy format
     gy = rng.uniform(-1, 1, (rois.shape[0], 8, 7, 7)).astype(np.float32)
     for path in ("auto", "generic", "table"):
-        _lib.set_tuning(force_path=PATHS[path])
+        opt = dict(force_path=PATHS[path])
         for S in (1, 2):
             outs, plan = _engine.forward([dev(x)], dev(rois), None, [0.5], [7], S,
-                                         _lib.COORD_CAFFE2, _lib.ROI_XY)
+                                         _lib.COORD_CAFFE2, _lib.ROI_XY, options=opt)
             w = oracle.forward_caffe2(x, rois, 7, 7, 0.5, S)
             assert oracle.rel_err(host(outs[0]), w) <= FWD_TOL, (path, S)
             g = _engine.backward(plan, [dev(gy)])
@@ -334,9 +331,8 @@ def test_edge_cases_caffe2_borders_and_degenerate():
                       np.float32)
     gyc = rng.uniform(-1, 1, (rois_c.shape[0], 8, 5, 7)).astype(np.float32)
     for path in ("auto", "generic"):
-        _lib.set_tuning(force_path=PATHS[path])
         outs, plan = _engine.forward([dev(x)], dev(rois_c), None, [0.5], [(5, 7)], 1,
-                                     _lib.COORD_CHAINER, _lib.ROI_XY)
+                                     _lib.COORD_CHAINER, _lib.ROI_XY, options=dict(force_path=PATHS[path]))
         w = oracle.forward_chainer(x, rois_c, 5, 7, 0.5)
         assert oracle.rel_err(host(outs[0]), w) <= FWD_TOL
         if path == "generic":
@@ -368,17 +364,16 @@ def test_empty_invalid_batch_and_level_clipping():
 
 def test_schedule_is_stable_binning_and_rows_keep_input_order():
     rng, feats, rois, levels, scales = make_case(seed=13, C=8, per_img=500)
-    for order_mode in (0, 1, 2, 3):
-        _lib.set_tuning(order=order_mode)
-        outs, _, plan = run_fused(feats, rois, None, scales, [7])
+    for order_mode in (_lib.SCHED_INPUT, _lib.SCHED_DEFAULT, _lib.SCHED_LEVEL_DESC, _lib.SCHED_COARSE_FIRST):
+        outs, _, plan = run_fused(feats, rois, None, scales, [7], options=dict(schedule=order_mode))
         lv, order = _engine.read_plan(plan)
         assert np.array_equal(lv, levels)
         img = rois[:, 0].astype(np.int64)
-        if order_mode == 0:
+        if order_mode == _lib.SCHED_INPUT:
             want = np.arange(len(lv))
-        elif order_mode == 1:
+        elif order_mode == _lib.SCHED_DEFAULT:
             want = np.argsort(img * 4 + lv, kind="stable")
-        elif order_mode == 2:
+        elif order_mode == _lib.SCHED_LEVEL_DESC:
             want = np.argsort(img * 4 + (3 - lv), kind="stable")
         else:
             want = np.argsort((3 - lv) * (img.max() + 1) + img, kind="stable")
@@ -411,8 +406,8 @@ def test_deterministic_backward_is_bit_reproducible_and_matches_oracle(mode_name
     gys = [synth.make_gy(rng, rois.shape[0], feats[0].shape[1], P) for P in sizes]
     _, ga, _ = run_fused(feats, rois, levels, scales, sizes, S, mode, gys=gys, deterministic=True)
     _, gb, _ = run_fused(feats, rois, levels, scales, sizes, S, mode, gys=gys, deterministic=True)
-    _lib.set_tuning(threads=256)
-    _, gc, _ = run_fused(feats, rois, levels, scales, sizes, S, mode, gys=gys, deterministic=True)
+    _, gc, _ = run_fused(feats, rois, levels, scales, sizes, S, mode, gys=gys, deterministic=True,
+                         options=dict(cta_threads=256))
     _, want = oracle_fused(feats, rois, levels, scales, sizes, S, mode_name, gys)
     for a, b, c, w in zip(ga, gb, gc, want):
         assert np.array_equal(a, b) and np.array_equal(a, c)
