@@ -67,10 +67,12 @@ class FusedStep(object):
             self._capture()
 
     # -- one step on the current stream ------------------------------------
-    def _launch(self):
+    def _launch(self, marks=None):
         with _engine._on(self.rois.device):
             cur = torch.cuda.current_stream(self.rois.device)
             ev = None
+            if marks:
+                marks[0].record(cur)
             if self.fork:
                 self._side.wait_stream(cur)                      # fork
                 with torch.cuda.stream(self._side):
@@ -79,11 +81,15 @@ class FusedStep(object):
             _, self.plan = _engine.forward(self.features, self.rois, self.levels, self.scales, self.sizes,
                                            sampling_ratio=self.sampling_ratio, roi_format=_lib.ROI_YX,
                                            options=self.options, workspace=self.workspace, out=self.outs)
+            if marks:
+                marks[1].record(cur)
             if self.gys is not None:
                 if ev is not None:
                     cur.wait_event(ev)                           # join
                 _engine.backward(self.plan, self.gys, out=self.grads, accumulate=self.fork,
                                  deterministic=self.deterministic)
+            if marks:
+                marks[2].record(cur)
 
     def _capture(self):
         dev = self.rois.device
@@ -99,9 +105,12 @@ class FusedStep(object):
                 self._launch()
             self.graph = g
 
-    def run(self):
-        if self.graph is not None:
+    def run(self, marks=None):
+        """One step on the current stream.  ``marks``: three CUDA events recorded before the
+        plan, after the forward launch and after the backward launch (measurement only;
+        launches from Python instead of replaying the graph)."""
+        if self.graph is not None and not marks:
             self.graph.replay()
         else:
-            self._launch()
+            self._launch(marks)
         return self.outs, self.grads

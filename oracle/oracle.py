@@ -18,7 +18,7 @@ __all__ = [
     "forward_chainer", "backward_chainer", "forward_caffe2", "backward_caffe2",
     "ref_caffe2_forward", "roi_yx_to_xy",
     "map_rois_to_fpn_levels", "level_area_thresholds", "levels_for_pyramid",
-    "fpn_forward", "fpn_backward", "rel_err",
+    "fpn_forward", "fpn_backward", "rel_err", "err_stats",
 ]
 
 _lib = None
@@ -276,3 +276,21 @@ def rel_err(a, b):
     if denom == 0.0:
         return float(np.max(np.abs(a))) if a.size else 0.0
     return float(np.max(np.abs(a - b)) / denom)
+
+
+def err_stats(a, b):
+    """Achieved errors of `a` against the oracle `b`, both readings of "relative error":
+      max_norm  max|a-b| / max|b|                       (rel_err, the gate of the parity tests)
+      elem_rel  max_i |a_i-b_i| / max(|b_i|, rms(b))    (element-wise, floored at the RMS
+                magnitude so that entries near zero do not divide by nothing)
+      max_abs   max|a-b|
+    """
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if b.size == 0:
+        return {"max_norm": 0.0, "elem_rel": 0.0, "max_abs": 0.0}
+    d = np.abs(a - b)
+    rms = float(np.sqrt(np.mean(b * b)))
+    floor = rms if rms > 0 else 1.0
+    return {"max_norm": rel_err(a, b), "elem_rel": float(np.max(d / np.maximum(np.abs(b), floor))),
+            "max_abs": float(d.max())}

@@ -23,6 +23,17 @@ _RPN_FILE = os.path.join(REFERENCE_ROOT, "chainer_maskrcnn", "model", "rpn",
                          "multilevel_region_proposal_network.py")
 
 
+def set_root(root):
+    """Points the loader at another copy of the reference files (baseline/_ref on the GPU
+    box, installed byte for byte by `make -C baseline ref`)."""
+    global REFERENCE_ROOT, _OP_FILE, _RPN_FILE, _cached
+    REFERENCE_ROOT = root
+    _OP_FILE = os.path.join(root, "chainer_maskrcnn", "functions", "roi_align", "roi_align_2d.py")
+    _RPN_FILE = os.path.join(root, "chainer_maskrcnn", "model", "rpn",
+                             "multilevel_region_proposal_network.py")
+    _cached = None
+
+
 def available():
     return os.path.exists(_OP_FILE)
 

@@ -238,6 +238,62 @@ def test_step_is_cuda_graph_capturable_and_replays_on_new_rois():
             assert oracle.rel_err(grads[l].cpu().numpy(), want_g[l]) <= 1e-4
 
 
+@pytest.mark.parametrize("graph", [True, False])
+@pytest.mark.parametrize("sizes,S", [([7], 2), ([7, 14], 1)])
+def test_fused_step_helper_forks_the_zero_fill_and_replays(graph, sizes, S):
+    """pkg.FusedStep: static buffers, gradient zero fill on a side stream (rpool_zero_fill +
+    accumulate), the step captured into a CUDA graph; new RoIs / gradients are written into
+    the same tensors between replays."""
+    rng = np.random.RandomState(12)
+    n_img, C, H, W, L = 2, 32, 160, 224, 4
+    feats = synth.make_pyramid(rng, n_img, C, H, W, L)
+    scales = [1.0 / s for s in synth.STRIDES[:L]]
+    rois_a = synth.make_rois(rng, n_img, 70, H, W, size_range=(8.0, 300.0))
+    rois_b = synth.make_rois(rng, n_img, 70, H, W, size_range=(8.0, 300.0))
+    gys = [synth.make_gy(rng, rois_a.shape[0], C, P) for P in sizes]
+    cl = lambda a: torch.from_numpy(a).cuda().contiguous(memory_format=torch.channels_last)
+    rois = torch.from_numpy(rois_a).cuda()
+    step = pkg.FusedStep([cl(f) for f in feats], rois, None, scales, sizes, S, gys=[cl(g) for g in gys],
+                         graph=graph)
+    assert (step.graph is not None) == graph
+    mode = "chainer" if S == 1 else "caffe2"
+    for r in (rois_a, rois_b, rois_a):
+        rois.copy_(torch.from_numpy(r).cuda())
+        for g in step.grads:
+            g.fill_(float("nan"))                 # the forked fill must overwrite everything
+        n0 = _lib.launch_count()
+        outs, grads = step.run()
+        torch.cuda.synchronize()
+        if not graph:
+            # plan + forward + zero fill + one backward launch per pooled size
+            assert _lib.launch_count() - n0 == 3 + len(sizes)
+        lv = oracle.levels_for_pyramid(r[:, 1:], L)
+        want_g = [np.zeros_like(f) for f in feats]
+        for o, P, gy in zip(outs, sizes, gys):
+            assert oracle.rel_err(o.cpu().numpy(), oracle.fpn_forward(feats, r, lv, scales, P, mode, S)) <= 1e-5
+            for l, part in enumerate(oracle.fpn_backward(gy, [f.shape for f in feats], r, lv, scales, mode, S)):
+                want_g[l] += part
+        for g, w in zip(grads, want_g):
+            assert oracle.rel_err(g.cpu().numpy(), w) <= 1e-4
+
+
+def test_backward_gpu_replans_when_the_rois_changed_in_place():
+    """the forward plan is reused in backward_gpu only for the same, unmodified
+    RoI tensor (storage, shape and version counter)."""
+    x, rois, gy, outh, outw, scale = _fixture(seed=3)
+    f = ROIAlign2D(outh, outw, scale)
+    xt, rt = torch.from_numpy(x).cuda(), torch.from_numpy(rois).cuda()
+    f.forward_gpu((xt, rt))
+    moved = rois.copy()
+    moved[:, 1:] = moved[:, 1:] * 0.5 + 0.5
+    rt.copy_(torch.from_numpy(moved).cuda())              # in place: same data_ptr
+    gx, _ = f.backward_gpu((None, rt), (torch.from_numpy(gy).cuda(),))
+    want = oracle.backward_chainer(gy, moved, x.shape, scale)
+    assert oracle.rel_err(gx.cpu().numpy(), want) <= 1e-4
+    gx2, _ = f.backward_gpu((None, rt[:5]), (torch.from_numpy(gy[:5]).cuda(),))     # a view: other shape
+    assert oracle.rel_err(gx2.cpu().numpy(), oracle.backward_chainer(gy[:5], moved[:5], x.shape, scale)) <= 1e-4
+
+
 def test_host_fused_call_and_launch_counter():
     rng = np.random.RandomState(4)
     feats = synth.make_pyramid(rng, 1, 16, 128, 128, 4)

@@ -360,6 +360,42 @@ def test_empty_invalid_batch_and_level_clipping():
     got = host(outs[0])
     assert np.all(got[2] == 0)
     assert oracle.rel_err(np.delete(got, 2, 0), want) <= FWD_TOL
+    # ... and both are flagged: the reference's NumPy path raises IndexError for such a RoI
+    flags = _engine.status_flags(plan)
+    assert flags & _lib.FLAG_BAD_BATCH and flags & _lib.FLAG_LEVEL_CLIPPED
+    with pytest.raises(IndexError):
+        _engine.check_rois(plan)
+    _, clean = _engine.forward(f, dev(rois), dev(levels), scales, [7])
+    assert _engine.status_flags(clean) == 0
+    _engine.check_rois(clean)
+    # levels in any integer / floating dtype (the heads cast with astype(int32))
+    base = host(_engine.forward(f, dev(rois), dev(levels), scales, [7])[0][0])
+    for t in (torch.int64, torch.int16, torch.uint8, torch.float64, torch.float16):
+        o, _ = _engine.forward(f, dev(rois), torch.from_numpy(levels).cuda().to(t), scales, [7])
+        assert np.array_equal(host(o[0]), base), t
+    with pytest.raises(TypeError):
+        _engine.forward(f, dev(rois), torch.from_numpy(levels).cuda() > 0, scales, [7])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two devices")
+def test_tensors_on_a_device_that_is_not_current():
+    """every launch (layout conversion included) must run on the tensors'
+    device and its stream, whatever torch's current device is."""
+    rng, feats, rois, levels, scales = make_case(seed=41, C=16, per_img=30)
+    d1 = torch.device("cuda", 1)
+    f1 = [torch.from_numpy(x).to(d1) for x in feats]                # NCHW: converted on device 1
+    gy = synth.make_gy(rng, rois.shape[0], 16, 7)
+    assert torch.cuda.current_device() == 0
+    outs, plan = _engine.forward(f1, torch.from_numpy(rois).to(d1), None, scales, [7], sampling_ratio=2)
+    grads = _engine.backward(plan, [torch.from_numpy(gy).to(d1)])
+    assert torch.cuda.current_device() == 0 and outs[0].device == d1 and grads[0].device == d1
+    torch.cuda.synchronize(d1)
+    want, wg = oracle_fused(feats, rois, levels, scales, [7], 2, "caffe2", [gy])
+    assert oracle.rel_err(host(outs[0]), want[0]) <= FWD_TOL
+    for g, w in zip(grads, wg):
+        assert oracle.rel_err(host(g), w) <= BWD_TOL
+    with pytest.raises(ValueError):
+        _engine.forward([x.cuda(0) for x in f1], torch.from_numpy(rois).to(d1), None, scales, [7])
 
 
 def test_schedule_is_stable_binning_and_rows_keep_input_order():
@@ -470,11 +506,25 @@ def test_layout_conversion_kernels():
 
 
 # ---------------------------------------------------------------------------
-# BASELINE.json sizes
+# BASELINE.json sizes: every kernel configuration, both coordinate recipes
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("cfg_id,mode_name,S", [(0, "chainer", 1), (0, "caffe2", 2),
-                                                (1, "chainer", 1), (1, "caffe2", 2)])
-def test_full_size_configs(cfg_id, mode_name, S):
+def _record(name, stats):
+    """Achieved errors go to gpurun_out/parity_achieved.json (the margin to the tolerances)."""
+    import json
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(path, exist_ok=True)
+    path = os.path.join(path, "parity_achieved.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+    except Exception:  # noqa: BLE001
+        d = {}
+    d[name] = stats
+    with open(path, "w") as f:
+        json.dump(d, f, indent=1, sort_keys=True)
+
+
+def _full_size_case(cfg_id):
     cfg = synth.CONFIGS[cfg_id]
     rng = np.random.RandomState(cfg_id)
     feats = synth.make_pyramid(rng, cfg["n_images"], cfg["channels"], cfg["height"], cfg["width"],
@@ -484,19 +534,95 @@ def test_full_size_configs(cfg_id, mode_name, S):
     L = cfg["n_levels"]
     levels = oracle.levels_for_pyramid(rois[:, 1:], L)
     scales = [1.0 / s for s in synth.STRIDES[:L]]
+    return cfg, rng, feats, rois, levels, scales
+
+
+@pytest.mark.parametrize("cfg_id,mode_name,S", [(0, "chainer", 1), (0, "caffe2", 2),
+                                                (1, "chainer", 1), (1, "caffe2", 2),
+                                                (2, "chainer", 1), (2, "caffe2", 2),
+                                                (3, "chainer", 1), (3, "caffe2", 2)])
+def test_full_size_configs(cfg_id, mode_name, S):
+    """configs[0..3] of BASELINE.json at full size against the oracle: mask head 14x14
+    (fpn_roi_mask_head.py:74-78), keypoint head 14x14 on person-shaped RoIs
+    (fpn_roi_keypoint_head.py:59-71,83-87), box 7x7 + mask 14x14 in one call on 16 images
+    (fpn_roi_mask_head.py:57-63,74-78).  Heads are checked one at a time so that only one
+    oracle result is alive at once (configs[3] pools 4 GB)."""
+    cfg, rng, feats, rois, levels, scales = _full_size_case(cfg_id)
     sizes = cfg["out_sizes"]
-    gys = [synth.make_gy(rng, rois.shape[0], cfg["channels"], P) for P in sizes]
+    C, R = cfg["channels"], rois.shape[0]
     mode = _lib.COORD_CHAINER if mode_name == "chainer" else _lib.COORD_CAFFE2
-    outs, grads, plan = run_fused(feats, rois, None, scales, sizes, S, mode, gys=gys)
+    f = [dev(x, True) for x in feats]
+    outs, plan = _engine.forward(f, dev(rois), None, scales, sizes, sampling_ratio=S, coord_mode=mode)
     lv, _ = _engine.read_plan(plan)
-    assert np.array_equal(lv, levels)
-    want, wgrads = oracle_fused(feats, rois, levels, scales, sizes, S, mode_name, gys)
-    for o, w in zip(outs, want):
-        assert oracle.rel_err(o, w) <= FWD_TOL
-    for g, w in zip(grads, wgrads):
-        assert oracle.rel_err(g, w) <= BWD_TOL
-    # adjoint identity <y, gy> == <x, gx> at full size (size-independent property)
-    lhs = sum(float((o.astype(np.float64) * g).sum()) for o, g in zip(outs, gys))
-    rhs = sum(float((f.astype(np.float64) * g).sum()) for f, g in zip(feats, grads))
-    scale = sum(float(np.abs(o.astype(np.float64) * g).sum()) for o, g in zip(outs, gys))
+    assert np.array_equal(lv, levels)                       # level assignment: bit-exact
+    assert _engine.status_flags(plan) == 0
+    gys_d = [torch.rand((R, C, P, P), device="cuda", generator=torch.Generator("cuda").manual_seed(P))
+             .mul_(2).sub_(1).contiguous(memory_format=torch.channels_last) for P in sizes]
+    grads = [host(g) for g in _engine.backward(plan, gys_d)]
+    torch.cuda.synchronize()
+    del f
+    shapes = [x.shape for x in feats]
+    lhs = scale = 0.0
+    wgrads = [np.zeros(s, np.float32) for s in shapes]
+    tag = "cfg%d_%s_S%d" % (cfg_id, mode_name, S)
+    for h, P in enumerate(sizes):
+        o, g = host(outs[h]), host(gys_d[h])
+        want = oracle.fpn_forward(feats, rois, levels, scales, P, mode_name, S, threads=oracle.max_threads())
+        st = oracle.err_stats(o, want)
+        _record("%s_fwd_%d" % (tag, P), st)
+        assert st["max_norm"] <= FWD_TOL and st["elem_rel"] <= FWD_TOL, (P, st)
+        del want
+        part = oracle.fpn_backward(g, shapes, rois, levels, scales, mode_name, S,
+                                   threads=oracle.max_threads())
+        for l in range(len(shapes)):
+            wgrads[l] += part[l]
+        # adjoint identity <y, gy> == <x, gx> at full size (size-independent property)
+        lhs += float((o.astype(np.float64) * g).sum())
+        scale += float(np.abs(o.astype(np.float64) * g).sum())
+        del o, g, part
+    for l, (g, w) in enumerate(zip(grads, wgrads)):
+        st = oracle.err_stats(g, w)
+        _record("%s_bwd_P%d" % (tag, l + 2), st)
+        assert st["max_norm"] <= BWD_TOL and st["elem_rel"] <= BWD_TOL, (l, st)
+    rhs = sum(float((x.astype(np.float64) * g).sum()) for x, g in zip(feats, grads))
     assert abs(lhs - rhs) <= 2e-7 * scale
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_by_image_equals_unsharded(world):
+    """BASELINE.json configs[3] dealt to 2/4/8 ranks by image (_sharding.shard_rois, image n
+    -> rank n mod world): every rank's pooled rows, put back at their global row numbers,
+    equal the unsharded run BIT FOR BIT, and every image's gradient matches the unsharded
+    one within the backward tolerance.  The ranks run one after the other on this device;
+    bench.py --shard repeats the check on real ranks."""
+    from chainer_maskrcnn_b200 import _sharding
+    cfg = dict(synth.CONFIGS[3], n_images=8, rois_per_image=500)        # same shapes, 8 images
+    rng = np.random.RandomState(33)
+    L, C, N = cfg["n_levels"], cfg["channels"], cfg["n_images"]
+    shapes = synth.pyramid_shapes(N, C, cfg["height"], cfg["width"], L)
+    rois = synth.make_rois(rng, N, cfg["rois_per_image"], cfg["height"], cfg["width"])
+    scales = [1.0 / s for s in synth.STRIDES[:L]]
+    sizes = cfg["out_sizes"]
+    gen = torch.Generator("cuda").manual_seed(5)
+    feats = [torch.randn(s, device="cuda", generator=gen).contiguous(memory_format=torch.channels_last)
+             for s in shapes]
+    gys = [torch.rand((rois.shape[0], C, P, P), device="cuda", generator=gen).mul_(2).sub_(1)
+           .contiguous(memory_format=torch.channels_last) for P in sizes]
+    outs, plan = _engine.forward(feats, dev(rois), None, scales, sizes, sampling_ratio=2)
+    grads = _engine.backward(plan, gys)
+    seen = np.zeros(rois.shape[0], np.int64)
+    for rank in range(world):
+        local, rows = _sharding.shard_rois(rois, N, world, rank)
+        mine = _sharding.images_of_rank(N, world, rank)
+        seen[rows] += 1
+        idx, ridx = torch.as_tensor(mine, device="cuda"), torch.as_tensor(rows, device="cuda")
+        f_loc = [f[idx].contiguous(memory_format=torch.channels_last) for f in feats]
+        g_loc = [g[ridx].contiguous(memory_format=torch.channels_last) for g in gys]
+        o_loc, p_loc = _engine.forward(f_loc, dev(local), None, scales, sizes, sampling_ratio=2)
+        gr_loc = _engine.backward(p_loc, g_loc)
+        for o, ol in zip(outs, o_loc):
+            assert torch.equal(o[ridx], ol), (world, rank)                 # forward: bit for bit
+        for l, (g, gl) in enumerate(zip(grads, gr_loc)):
+            st = oracle.err_stats(host(gl), host(g[idx]))
+            assert st["max_norm"] <= BWD_TOL and st["elem_rel"] <= BWD_TOL, (world, rank, l, st)
+    assert np.all(seen == 1)                                                # every RoI on exactly one rank
