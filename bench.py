@@ -679,7 +679,7 @@ def run_b200(args):
 
     # ---- the step: the package's helper (static buffers, forked zero fill, CUDA graph) ----
     step = pkg.FusedStep(feats, rois, None, scales, sizes, S, gys=gys,
-                         graph=not (args.no_graph or args.deterministic), deterministic=args.deterministic,
+                         graph=not args.no_graph, deterministic=args.deterministic,
                          fork_zero_fill=not args.no_fork, options=opts)
     n0 = _lib.launch_count()
     step.run(marks=[torch.cuda.Event() for _ in range(3)])       # launched from Python: counted
@@ -850,7 +850,7 @@ def run_b200(args):
             gpu_base = gpu_baseline_arm(args.config, args.gpu_baseline_rois, device)
         except Exception as e:  # noqa: BLE001
             gpu_base = {"value": None, "unit": UNIT, "kind": "failed: %r" % (e,)}
-    graphed = not (args.no_graph or args.deterministic)
+    graphed = not args.no_graph
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": step_ms, "higher_is_better": True,

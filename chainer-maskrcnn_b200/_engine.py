@@ -145,7 +145,7 @@ def _fill_problem(plan, level_ptrs, pooled_ptrs, accumulate=False, deterministic
         for h, ptr in enumerate(pooled_ptrs):
             p.pooled[h] = ptr
         p.accumulate = int(accumulate)
-        p.deterministic = int(deterministic)
+        p.deterministic = int(bool(deterministic))
         p.det_workspace = None
         p.det_workspace_bytes = 0
         return p
@@ -177,7 +177,7 @@ def _fill_problem(plan, level_ptrs, pooled_ptrs, accumulate=False, deterministic
     p.sampling_ratio = plan.sampling_ratio
     p.coord_mode = plan.coord_mode
     p.accumulate = int(accumulate)
-    p.deterministic = int(deterministic)
+    p.deterministic = int(bool(deterministic))
     p.opt = _lib.make_options(**plan.options)
     return p
 
@@ -314,11 +314,16 @@ def forward(features, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
     return outs, plan
 
 
-def backward(plan, gys, deterministic=False, out=None, accumulate=False):
+def backward(plan, gys, deterministic=False, out=None, accumulate=False, check_flags=True):
     """Dense feature gradients (channels-last memory, logical (N,C,H,W)) for
     every level from the pooled gradients ``gys`` (one per head).  ``out``: optional
     preallocated gradient tensors to write into; with ``accumulate=True`` the result
-    is added to what ``out`` already holds (no zero fill: rpool_problem.accumulate)."""
+    is added to what ``out`` already holds (no zero fill: rpool_problem.accumulate).
+    ``deterministic``: every gradient cell is summed by one owner in schedule order
+    (bit-identical from run to run; one launch, no scratch).  RoIs that need the generic
+    kernel path cannot be ordered: they are skipped and reported -- ``check_flags`` reads
+    the flag back (one stream synchronisation) and raises; pass False inside CUDA-graph
+    capture and call ``status_flags(plan)`` afterwards."""
     if accumulate and out is None:
         raise ValueError("accumulate=True needs the gradient tensors to add into (out=...)")
     if len(gys) != len(plan.out_sizes):
@@ -352,9 +357,10 @@ def backward(plan, gys, deterministic=False, out=None, accumulate=False):
     L = _lib.lib()
     with _on(plan.device):
         ws, ws_n = plan.workspace.data_ptr(), plan.workspace.numel()
-        if deterministic:
-            # the scratch holds one private window per RoI: its size depends on the
-            # RoIs and is computed on the device (this query synchronises the stream)
+        if deterministic == "scratch":
+            # r01 variant (private windows + ordered gather), kept for comparison: the scratch
+            # holds one private window per RoI, its size depends on the RoIs and is computed
+            # on the device (this query synchronises the stream)
             need = ctypes.c_size_t(0)
             _lib.check(L.rpool_backward_det_bytes(ctypes.byref(prob), ws, ws_n, _stream(),
                                                   ctypes.byref(need)))
@@ -362,7 +368,7 @@ def backward(plan, gys, deterministic=False, out=None, accumulate=False):
             prob.det_workspace = scratch.data_ptr()
             prob.det_workspace_bytes = need.value
         _lib.check(L.rpool_backward(ctypes.byref(prob), ws, ws_n, _stream()))
-        if deterministic:
+        if deterministic and check_flags:
             err = ctypes.c_int32(0)
             _lib.check(L.rpool_status_flags(ws, R, _stream(), ctypes.byref(err)))
             if err.value & (_lib.FLAG_DET_GENERIC | _lib.FLAG_DET_SCRATCH):

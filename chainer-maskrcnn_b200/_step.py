@@ -57,13 +57,12 @@ class FusedStep(object):
         coord = _engine.default_coord_mode(self.sampling_ratio)
         n = _lib.lib().rpool_workspace_bytes_ex(R, len(self.sizes), coord)
         self.workspace = torch.empty(n, dtype=torch.uint8, device=dev)
-        # the deterministic variant sizes its scratch from the RoIs with a host round trip:
-        # it cannot fork the fill (it writes every cell itself) nor be captured
+        # the deterministic variant writes every gradient cell itself: nothing to fork
         self.fork = bool(fork_zero_fill) and self.gys is not None and not self.deterministic
         self._side = torch.cuda.Stream(device=dev) if self.fork else None
         self.plan = None
         self.graph = None
-        if graph and not self.deterministic:
+        if graph:
             self._capture()
 
     # -- one step on the current stream ------------------------------------
@@ -86,8 +85,9 @@ class FusedStep(object):
             if self.gys is not None:
                 if ev is not None:
                     cur.wait_event(ev)                           # join
+                # (no flag read-back inside the step: it would synchronise; see status_flags)
                 _engine.backward(self.plan, self.gys, out=self.grads, accumulate=self.fork,
-                                 deterministic=self.deterministic)
+                                 deterministic=self.deterministic, check_flags=False)
             if marks:
                 marks[2].record(cur)
 

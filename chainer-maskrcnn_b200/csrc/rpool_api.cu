@@ -8,7 +8,7 @@
 #include <cstdio>
 #include <cstring>
 
-#include "rpool_kernels.cuh"
+#include "rpool_det.cuh"
 
 using namespace rpool;
 
@@ -245,11 +245,18 @@ int fill_params(const rpool_problem *p, const Workspace &w, const Options &o, bo
     return ctl + p->n_heads * ttab + warps * k.strip_cols * 512;
 }
 
+// Dynamic shared memory of the "stream" kernels: the RoI record + one ring / double buffer per warp.
+int stream_smem(const rpool_problem *p, bool bwd, int threads)
+{
+    const int ctl = (rec_bytes(p->n_heads) + 127) & ~127;
+    return ctl + (threads / 32) * (bwd ? kBwdStreamWarpBytes : kFwdStreamWarpBytes);
+}
+
 // Raises a pooling kernel's dynamic shared memory limit.  The limit is per device
 // and only ever needs to grow, so the largest value set so far is remembered per
 // (kernel, device) and the driver call is skipped when it already covers `smem`.
 constexpr int kSmemCacheDevices = 64;
-std::atomic<int> g_smem_set[2][kSmemCacheDevices];
+std::atomic<int> g_smem_set[4][kSmemCacheDevices];
 
 template <typename Kern>
 int set_smem(Kern kern, int which, int smem)
@@ -402,6 +409,15 @@ int rpool_forward(const rpool_problem *p, void *ws, size_t ws_size, void *stream
         return fail(RPOOL_ERR_UNSUPPORTED, "forward needs %d bytes of shared memory; the limit is %d",
                     smem, kMaxSmem);
     k.variant = o.var_fwd;
+    if (o.var_fwd == kVariantStream) {
+        const int smem2 = stream_smem(p, false, threads);
+        rc = set_smem(rpool_forward_stream_kernel, 2, smem2);
+        if (rc) return rc;
+        rpool_forward_stream_kernel<<<p->n_rois, threads, smem2, static_cast<cudaStream_t>(stream)>>>(k);
+        CUDA_TRY(cudaGetLastError(), "rpool_forward_stream_kernel launch");
+        g_launches++;
+        return RPOOL_OK;
+    }
     rc = set_smem(rpool_forward_kernel, 0, smem);
     if (rc) return rc;
     rpool_forward_kernel<<<p->n_rois, threads, smem, static_cast<cudaStream_t>(stream)>>>(k);
@@ -484,10 +500,72 @@ int rpool_status_flags(const void *ws, int32_t n_rois, void *stream, int32_t *fl
     return RPOOL_OK;
 }
 
+// Deterministic backward, owner-gathers formulation (rpool_det.cuh): one launch, no scratch.
+static int backward_det_owner(const rpool_problem *p, void *ws, const Options &o, cudaStream_t st)
+{
+    if (o.order != RPOOL_SCHED_DEFAULT)
+        return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward needs the (image, level) schedule "
+                    "(opt.schedule = RPOOL_SCHED_DEFAULT)");
+    if (p->feat_layout != RPOOL_NHWC || p->pool_layout != RPOOL_NHWC || (p->channels & 3))
+        return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward needs channels-last tensors with C %% 4 == 0");
+    int nimg = 1;
+    for (int l = 0; l < p->n_levels; ++l) nimg = p->level[l].n_images > nimg ? p->level[l].n_images : nimg;
+    if (nimg * p->n_levels > kPlanMaxKeys)
+        return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward: images x levels = %d exceeds %d",
+                    nimg * p->n_levels, kPlanMaxKeys);
+    for (int h = 0; h < p->n_heads; ++h)
+        if (p->out_h[h] > kPMax || p->out_w[h] > kPMax)
+            return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward: pooled size %dx%d exceeds %d",
+                        p->out_h[h], p->out_w[h], kPMax);
+    for (int l = 0; l < p->n_levels; ++l)
+        if ((reinterpret_cast<uintptr_t>(p->level[l].data) & 15))
+            return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward: level %d gradient is not 16-byte aligned", l);
+    for (int h = 0; h < p->n_heads; ++h)
+        if (p->n_rois > 0 && (reinterpret_cast<uintptr_t>(p->pooled[h]) & 15))
+            return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward: gy %d is not 16-byte aligned", h);
+    const Workspace w = ws_split(ws, p);
+    DetParams d;
+    memset(&d, 0, sizeof(d));
+    long long ctas = 0;
+    for (int li = 0; li < p->n_levels; ++li) {
+        const int l = p->n_levels - 1 - li;          // coarse levels first: their strips are the longest
+        d.lvl[l].data = static_cast<float *>(p->level[l].data);
+        d.lvl[l].n_images = p->level[l].n_images;
+        d.lvl[l].H = p->level[l].height;
+        d.lvl[l].W = p->level[l].width;
+        const int row_tiles = (p->level[l].width + kSW - 1) / kSW;
+        d.tiles[l] = (row_tiles + 7) / 8;            // at most 8 CTAs per map row
+        d.strips[l] = (row_tiles + d.tiles[l] - 1) / d.tiles[l];
+        d.cta_base[li] = ctas;
+        ctas += (long long)p->level[l].n_images * p->level[l].height * d.strips[l];
+    }
+    d.cta_base[p->n_levels] = ctas;
+    if (ctas > 2147483647ll) return fail(RPOOL_ERR_UNSUPPORTED, "pyramid too large for the gather launch");
+    d.n_levels = p->n_levels;
+    d.C = p->channels;
+    d.accumulate = p->accumulate;
+    d.n_heads = p->n_heads;
+    for (int h = 0; h < p->n_heads; ++h) {
+        d.PH[h] = p->out_h[h];
+        d.PW[h] = p->out_w[h];
+        d.gy[h] = static_cast<const float *>(p->pooled[h]);
+    }
+    d.gstart = w.gstart;
+    d.recs = w.recs_bwd;
+    d.rec_stride = w.rec_stride;
+    d.R = p->n_rois;
+    d.det_err = w.det_err;
+    if (p->n_rois == 0)    // no plan ran: the flag word was never cleared
+        CUDA_TRY(cudaMemsetAsync(w.det_err, 0, sizeof(int), st), "cudaMemsetAsync(det_err)");
+    rpool_backward_det_kernel<<<(unsigned)ctas, kDetThreads, 0, st>>>(d);
+    CUDA_TRY(cudaGetLastError(), "rpool_backward_det_kernel launch");
+    g_launches++;
+    return RPOOL_OK;
+}
+
 static int backward_det(const rpool_problem *p, void *ws, const Options &o, cudaStream_t st)
 {
-    if (!p->det_workspace) return fail(RPOOL_ERR_WORKSPACE, "deterministic backward: det_workspace is NULL "
-                                       "(size it with rpool_backward_det_bytes)");
+    if (!p->det_workspace) return backward_det_owner(p, ws, o, st);
     if (reinterpret_cast<uintptr_t>(p->det_workspace) & 15)
         return fail(RPOOL_ERR_INVALID, "det_workspace must be 16-byte aligned");
     KParams k;
@@ -622,6 +700,18 @@ int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *strea
         k.rec_head = parts > 1 ? part : 0;
         k.rec_stride = w.rec_stride;       // records keep the layout of the plan's head count
         k.variant = o.var_bwd;
+        bool wide = false;       // the stream kernel's double buffer holds bin rows of <= kPBwd bins
+        for (int h = 0; h < q.n_heads; ++h) wide = wide || q.out_w[h] > kPBwd;
+        if (o.var_bwd == kVariantStream && !wide) {
+            threads = o.threads;
+            const int smem2 = stream_smem(&q, true, threads);
+            rc = set_smem(rpool_backward_stream_kernel, 3, smem2);
+            if (rc) return rc;
+            rpool_backward_stream_kernel<<<p->n_rois, threads, smem2, st>>>(k);
+            CUDA_TRY(cudaGetLastError(), "rpool_backward_stream_kernel launch");
+            g_launches++;
+            continue;
+        }
         rc = set_smem(rpool_backward_kernel, 1, smem);
         if (rc) return rc;
         rpool_backward_kernel<<<p->n_rois, threads, smem, st>>>(k);

@@ -852,7 +852,7 @@ __device__ __forceinline__ int plan_key(const PlanParams &p, int i, int &lvl_out
     else if (p.given_levels_f32) lvl = (int)__ldg(p.given_levels_f32 + i);  // astype(int32)
     else lvl = level_from_area(q.y1, q.x1, q.y2, q.x2, p.thr, p.n_thr, p.k_min);
     int flags = 0;
-    if (lvl < 0 || lvl >= L) flags |= RPOOL_FLAG_LEVEL_CLIPPED;
+    if ((p.given_levels || p.given_levels_f32) && (lvl < 0 || lvl >= L)) flags |= RPOOL_FLAG_LEVEL_CLIPPED;
     lvl = lvl < 0 ? 0 : (lvl >= L ? L - 1 : lvl);
     if (q.b < 0 || q.b >= p.n_images) flags |= RPOOL_FLAG_BAD_BATCH;
     const int b = q.b < 0 ? 0 : (q.b >= p.n_images ? p.n_images - 1 : q.b);

@@ -248,7 +248,7 @@ RPOOL_API int rpool_backward_det_bytes(const rpool_problem *problem, void *works
  * roi_align_2d.py:76-86) is computed safely here and flagged instead.
  * rpool_status_flags copies them to the host and SYNCHRONISES `stream`. */
 #define RPOOL_FLAG_BAD_BATCH 1     /* a RoI's batch index is outside [0, n_images): zero rows, no gradient */
-#define RPOOL_FLAG_LEVEL_CLIPPED 2 /* a given level was outside the pyramid and was clipped (maskrcnn.py:141) */
+#define RPOOL_FLAG_LEVEL_CLIPPED 2 /* informational: a GIVEN level was outside the pyramid and was clipped like maskrcnn.py:141 */
 #define RPOOL_FLAG_DET_GENERIC 4   /* deterministic backward: a RoI needs the generic path and was skipped */
 #define RPOOL_FLAG_DET_SCRATCH 8   /* deterministic backward: det_workspace does not match the plan */
 RPOOL_API int rpool_status_flags(const void *workspace, int32_t n_rois, void *stream,

@@ -137,8 +137,7 @@ def test_workspace_errors_without_gpu():
     q = _problem()
     q.level[0].data = None
     assert L.rpool_zero_fill(ctypes.byref(q), None) == 1
-    # the deterministic variant needs its scratch (sized by rpool_backward_det_bytes)
-    # and channels-last tensors
+    # the deterministic variant needs channels-last tensors and the default schedule
     p = _problem(deterministic=1)
     n = L.rpool_workspace_bytes_ex(p.n_rois, p.n_heads, p.coord_mode)
     assert 0 < n <= L.rpool_workspace_bytes(p.n_rois)
@@ -148,10 +147,13 @@ def test_workspace_errors_without_gpu():
     assert b"needed" in L.rpool_last_error()
     assert L.rpool_backward(ctypes.byref(p), ctypes.c_void_p(ws.value + 4), n, None) == 3
     assert b"aligned" in L.rpool_last_error()
-    assert L.rpool_backward(ctypes.byref(p), ws, n, None) == 3
-    assert b"det_workspace" in L.rpool_last_error()
-    p = _problem(deterministic=1, det_workspace=0x4000, det_workspace_bytes=1 << 20, feat_layout=1)
+    p = _problem(deterministic=1, feat_layout=1)
     assert L.rpool_backward(ctypes.byref(p), ws, n, None) == 2
+    assert b"channels-last" in L.rpool_last_error()
+    p = _problem(deterministic=1)
+    p.opt = _lib.make_options(schedule=_lib.SCHED_INPUT)
+    assert L.rpool_backward(ctypes.byref(p), ws, n, None) == 2
+    assert b"schedule" in L.rpool_last_error()
 
 
 def test_launch_without_gpu_fails_loudly():

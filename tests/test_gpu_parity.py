@@ -466,10 +466,30 @@ def test_deterministic_backward_edge_cases():
     gd = [host(g) for g in _engine.backward(plan, [dev(gy)], deterministic=True)]
     for a, d in zip(ga, gd):
         assert oracle.rel_err(d, a) <= BWD_TOL
-    # pooled size 20 > 16 needs the generic path, which cannot be ordered: loud error
-    outs, plan = _engine.forward(f, dev(rois), None, scales, [20])
+    # pooled size 20 (beyond the atomic table path's 16) is fine for the owner-gathers kernel
+    outs, plan = _engine.forward(f, dev(rois), None, scales, [20], sampling_ratio=2)
+    gy20 = synth.make_gy(rng, rois.shape[0], 8, 20)
+    gd = [host(g) for g in _engine.backward(plan, [dev(gy20)], deterministic=True)]
+    _, want = oracle_fused(feats, rois, levels, scales, [20], 2, "caffe2", [gy20])
+    for d, w in zip(gd, want):
+        assert oracle.rel_err(d, w) <= BWD_TOL
+    # pooled size 40 > 32 has no tables at all, and a map narrower than 8 columns takes the generic
+    # path, which cannot be ordered: loud errors, never a silently unordered result
+    outs, plan = _engine.forward(f, dev(rois), None, scales, [40])
     with pytest.raises(_lib.RpoolError):
-        _engine.backward(plan, [dev(synth.make_gy(rng, rois.shape[0], 8, 20))], deterministic=True)
+        _engine.backward(plan, [dev(synth.make_gy(rng, rois.shape[0], 8, 40))], deterministic=True)
+    x = rng.standard_normal((1, 8, 12, 6)).astype(np.float32)
+    r1 = np.array([[0, 1, 1, 9, 4], [0, 2, 0, 11, 5]], np.float32)
+    outs, plan = _engine.forward([dev(x)], dev(r1), None, [1.0], [7])
+    with pytest.raises(_lib.RpoolError):
+        _engine.backward(plan, [dev(synth.make_gy(rng, 2, 8, 7))], deterministic=True)
+    assert _engine.status_flags(plan) & _lib.FLAG_DET_GENERIC
+    # the r01 formulation (private windows + ordered gather) is still reachable and agrees
+    outs, plan = _engine.forward(f, dev(r2), None, scales, [7], sampling_ratio=2)
+    gs = [host(g) for g in _engine.backward(plan, [dev(gy)], deterministic="scratch")]
+    gd = [host(g) for g in _engine.backward(plan, [dev(gy)], deterministic=True)]
+    for a, d in zip(gs, gd):
+        assert oracle.rel_err(d, a) <= BWD_TOL
 
 
 @pytest.mark.parametrize("deterministic", [False, True])

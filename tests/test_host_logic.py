@@ -39,6 +39,30 @@ def test_reference_names_and_signatures():
         ["self", "levels", "indices_and_rois", "spatial_scales"]
 
 
+def test_chainer_adapter_is_import_guarded():
+    """chainer / cupy are absent here: the adapter says so instead of half-importing."""
+    import importlib
+    import sys
+    if "chainer" in sys.modules or importlib.util.find_spec("chainer") is not None:
+        pytest.skip("chainer is installed")
+    with pytest.raises(ImportError, match="needs chainer and cupy"):
+        importlib.import_module("chainer_maskrcnn_b200.chainer_adapter")
+
+
+def test_caffe2_module_shim_has_the_reference_signature():
+    # caffe2_roi_align.cpp:231: forward(bottom_data, bottom_rois, out_h, out_w, spatial_scale)
+    import importlib.util
+    path = os.path.join(ROOT, "chainer-maskrcnn_b200", "dropin", "caffe2_roi_align.py")
+    spec = importlib.util.spec_from_file_location("_shim_caffe2_roi_align", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert list(inspect.signature(mod.forward).parameters) == \
+        ["bottom_data", "bottom_rois", "out_h", "out_w", "spatial_scale"]
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):          # no device: loud, never a CPU result
+            mod.forward(np.zeros((1, 4, 8, 8), np.float32), np.zeros((1, 5), np.float32), 2, 2, 1.0)
+
+
 def test_pyramid_constants():
     assert fpn.feat_strides == [4, 8, 16, 32, 64]          # feature_pyramid_network.py:9
     assert fpn.spatial_scales == [1 / 4, 1 / 8, 1 / 16, 1 / 32, 1 / 64]
