@@ -377,10 +377,10 @@ int rpool_plan(const rpool_problem *p, void *ws, size_t ws_size, void *stream)
     k.levels = w.levels; k.order = w.order; k.keys = w.keys; k.bh = w.bh; k.gstart = w.gstart;
     k.rflags = w.rflags;
     k.det_err = w.det_err;
-    // R <= kKeyBlock: one launch (every plan CTA ranks its RoI against all the others itself);
+    // R <= kPlanSingle: one launch (every plan warp ranks its RoI against all the others itself);
     // larger sets get their keys and per-block histograms from rpool_keys_kernel first
     k.n_blocks = 0;
-    if (p->n_rois > kKeyBlock && o.order != RPOOL_SCHED_INPUT) {
+    if (p->n_rois > kPlanSingle && o.order != RPOOL_SCHED_INPUT) {
         k.n_blocks = (int)ws_key_blocks(p->n_rois);
         rpool_keys_kernel<<<k.n_blocks, kKeyBlock, 0, st>>>(k);
         CUDA_TRY(cudaGetLastError(), "rpool_keys_kernel launch");
@@ -388,7 +388,7 @@ int rpool_plan(const rpool_problem *p, void *ws, size_t ws_size, void *stream)
     }
     KParams kp;
     fill_params(p, w, o, false, kPlanThreads, kp);
-    rpool_plan_kernel<<<p->n_rois, kPlanThreads, 0, st>>>(kp, k, w.recs_fwd, w.recs_bwd);
+    rpool_plan_kernel<<<(p->n_rois + kPlanWarps - 1) / kPlanWarps, kPlanThreads, 0, st>>>(kp, k, w.recs_fwd, w.recs_bwd);
     CUDA_TRY(cudaGetLastError(), "rpool_plan_kernel launch");
     g_launches++;
     return RPOOL_OK;
@@ -557,7 +557,7 @@ static int backward_det_owner(const rpool_problem *p, void *ws, const Options &o
     d.det_err = w.det_err;
     if (p->n_rois == 0)    // no plan ran: the flag word was never cleared
         CUDA_TRY(cudaMemsetAsync(w.det_err, 0, sizeof(int), st), "cudaMemsetAsync(det_err)");
-    rpool_backward_det_kernel<<<(unsigned)ctas, kDetThreads, 0, st>>>(d);
+    rpool_backward_det_kernel<<<(unsigned)ctas, kDetThreads, sizeof(DetShared), st>>>(d);
     CUDA_TRY(cudaGetLastError(), "rpool_backward_det_kernel launch");
     g_launches++;
     return RPOOL_OK;

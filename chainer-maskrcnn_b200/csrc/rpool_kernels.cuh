@@ -100,38 +100,6 @@ __device__ __forceinline__ bool pointers_aligned(const KParams &P, const LevelDe
     return ok;
 }
 
-// Builds the footprint tables of one RoI in `ctl` (any CTA size); returns with
-// the CTA synchronised.  Clears kRecFits when a footprint does not fit kNT cells.
-__device__ __forceinline__ void build_tables(const KParams &P, const RoiCtx &c, bool bwd, BlockCtl *ctl)
-{
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        ctl->wmin[0] = ctl->wmin[1] = 0x7fffffff;
-        ctl->wmax[0] = ctl->wmax[1] = -1;
-        for (int h = 0; h < kMaxHeads; ++h) ctl->hd[h].nmax[0] = ctl->hd[h].nmax[1] = 0;
-    }
-    __syncthreads();
-    int total = 0;
-    for (int h = 0; h < P.n_heads; ++h) total += P.PH[h] + P.PW[h];
-    // entry e -> (head, axis, bin)
-    for (int e0 = tid; e0 < total; e0 += blockDim.x) {
-        int h = 0, e = e0;
-        while (e >= P.PH[h] + P.PW[h]) { e -= P.PH[h] + P.PW[h]; ++h; }
-        const int ny = P.PH[h];
-        const int axis = e < ny ? 0 : 1;
-        const int p = axis ? e - ny : e;
-        int lo, hi;
-        const bool ok = fill_axis_entry(ctl->hd[h].tab[axis], axis_of(P, c, bwd, h, axis), P.mode, p, lo, hi);
-        if (!ok) atomicAnd(&ctl->flags, ~kRecFits);
-        if (hi >= lo) {
-            atomicMin(&ctl->wmin[axis], lo);
-            atomicMax(&ctl->wmax[axis], hi);
-            atomicMax(&ctl->hd[h].nmax[axis], hi - lo + 1);
-        }
-    }
-    __syncthreads();
-}
-
 // ---------------------------------------------------------------------------
 // generic path (reference operation order; any layout)
 // ---------------------------------------------------------------------------
@@ -406,48 +374,6 @@ __device__ __forceinline__ void fwd_tasks(const KParams &P, const RoiCtx &c, con
             else fwd_bin_pass<4>(V, cnt, wp, o_ptr, C, active);
         }
     }
-}
-
-// Cuts every head's bins into chunks whose x footprints fit a span of kSW
-// columns; records per chunk its first bin, the first column of the span and how
-// many of its bins start at each of the kSW offsets (one byte per offset).
-// max_bins bounds the bins per chunk (the backward pass keeps them in registers).
-__device__ __forceinline__ void build_chunks(const KParams &P, const RoiCtx &c, BlockCtl *ctl, int max_bins)
-{
-    if (threadIdx.x < P.n_heads) {
-        const int h = threadIdx.x;
-        const AxisTab &xt = ctl->hd[h].tab[1];
-        const int PW = P.PW[h];
-        const int W = c.L.W;
-        int NX = ctl->hd[h].nmax[1];
-        NX = NX < 1 ? 1 : NX;
-        int n = 0, pa = 0;
-        while (pa < PW) {
-            ctl->hd[h].cstart[n] = (unsigned char)pa;
-            const int lo_a = xt.lo[pa];
-            int x0 = lo_a < W - kSW ? lo_a : W - kSW;   // span [x0, x0 + kSW) inside the image
-            x0 = x0 < 0 ? 0 : x0;
-            unsigned long long cnt = 0;
-            unsigned mask = 0;
-            int pb = pa;
-            while (pb < PW && pb - pa < max_bins) {
-                const int last = xt.lo[pb] + NX - 1;
-                const int lim = last < W - 1 ? last : W - 1;   // taps beyond the image carry no weight
-                if (pb > pa && lim - x0 >= kSW) break;
-                cnt += 1ull << (8 * (xt.lo[pb] - x0));
-                mask |= ((1u << xt.n[pb]) - 1u) << (xt.lo[pb] - x0);
-                ++pb;
-            }
-            ctl->hd[h].cx0[n] = x0;
-            ctl->hd[h].ccnt[n] = cnt;
-            ctl->hd[h].cmask[n] = (unsigned char)(mask & 0xffu);
-            ++n;
-            pa = pb;
-        }
-        ctl->hd[h].cstart[n] = (unsigned char)PW;
-        ctl->hd[h].nchunk = n;
-    }
-    __syncthreads();
 }
 
 __device__ __forceinline__ void ctx_from_record(const KParams &P, const BlockCtl *ctl, RoiCtx &c)
@@ -790,15 +716,16 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
 // ---------------------------------------------------------------------------
 // plan: level assignment + stable (image, level) binning + every RoI's record
 // ---------------------------------------------------------------------------
-// One 64-thread CTA per input RoI i (all RoIs in parallel, one wave for the sizes of
-// BASELINE.json).  The CTA finds its RoI's slot in the launch schedule -- the stable
+// One warp per input RoI i, four to a CTA (all RoIs in parallel, one wave for the sizes
+// of BASELINE.json; nothing in a RoI's plan needs more than warp-wide cooperation, so
+// there is no CTA barrier on the path).  The warp finds its RoI's slot in the launch schedule -- the stable
 // rank of (key_i, i) among all RoIs, key = (image, level) in the order the schedule
 // asks for -- and writes the RoI's record (footprint tables + chunking, for the
 // forward geometry and, in RPOOL_COORD_CHAINER mode, a second one for the backward
 // geometry) at that slot.  There is no single-CTA sort on the critical path:
-//   R <= kKeyBlock   one launch: every CTA derives the keys of all RoIs itself
-//                    (R / 64 RoIs per thread, 20 bytes each, L1/L2 hits);
-//   R  > kKeyBlock   rpool_keys_kernel first writes the keys and one histogram per
+//   R <= kPlanSingle one launch: every warp derives the keys of all RoIs itself
+//                    (R / 32 RoIs per lane, 20 bytes each, L1/L2 hits);
+//   R  > kPlanSingle rpool_keys_kernel first writes the keys and one histogram per
 //                    block of kKeyBlock RoIs; a plan CTA then sums the histogram
 //                    entries that precede (key_i, block_i) and ranks its RoI inside
 //                    its own block.
@@ -838,9 +765,11 @@ __device__ __forceinline__ int level_from_area(float y1, float x1, float y2, flo
     return k;
 }
 
-constexpr int kPlanThreads = 64;
+constexpr int kPlanWarps = 4;               // RoIs per plan CTA: one warp each
+constexpr int kPlanThreads = kPlanWarps * 32;
 constexpr int kPlanMaxKeys = 256;
-constexpr int kKeyBlock = 1024;
+constexpr int kKeyBlock = 1024;             // RoIs per block of rpool_keys_kernel
+constexpr int kPlanSingle = 512;            // up to this many RoIs every plan warp derives all keys itself
 
 // Level (clipped to the pyramid, maskrcnn.py:141), schedule key and flags of RoI i.
 __device__ __forceinline__ int plan_key(const PlanParams &p, int i, int &lvl_out, int &flags_out)
@@ -884,64 +813,128 @@ rpool_keys_kernel(const __grid_constant__ PlanParams p)
     for (int k = tid; k < p.K; k += kKeyBlock) p.bh[blockIdx.x * p.K + k] = hist[k];
 }
 
-__device__ __forceinline__ int plan_cta_sum(int v, int *scratch)
+// Footprint tables of one RoI by one warp: entries (pooled size, axis, bin) are dealt to
+// the lanes, the window extent and the widest footprints are warp reductions.
+__device__ __forceinline__ void warp_build_tables(const KParams &P, const RoiCtx &c, bool bwd, BlockCtl *ctl,
+                                                  int lane)
 {
-    // sum over the CTA's two warps
+    int total = 0;
+    for (int h = 0; h < P.n_heads; ++h) total += P.PH[h] + P.PW[h];
+    int wmin[2] = {0x7fffffff, 0x7fffffff}, wmax[2] = {-1, -1};
+    int nmax[kMaxHeads][2];
+    for (int h = 0; h < kMaxHeads; ++h) nmax[h][0] = nmax[h][1] = 0;
+    bool fits = true;
+    for (int e0 = lane; e0 < total; e0 += 32) {
+        int h = 0, e = e0;
+        while (e >= P.PH[h] + P.PW[h]) { e -= P.PH[h] + P.PW[h]; ++h; }
+        const int ny = P.PH[h];
+        const int axis = e < ny ? 0 : 1;
+        const int pbin = axis ? e - ny : e;
+        int lo, hi;
+        fits = fill_axis_entry(ctl->hd[h].tab[axis], axis_of(P, c, bwd, h, axis), P.mode, pbin, lo, hi) && fits;
+        if (hi >= lo) {
+            wmin[axis] = lo < wmin[axis] ? lo : wmin[axis];
+            wmax[axis] = hi > wmax[axis] ? hi : wmax[axis];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-    __syncthreads();
-    return scratch[0] + scratch[1];
+            for (int hh = 0; hh < kMaxHeads; ++hh)
+                if (hh == h) nmax[hh][axis] = hi - lo + 1 > nmax[hh][axis] ? hi - lo + 1 : nmax[hh][axis];
+        }
+    }
+    fits = __all_sync(0xffffffffu, fits);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        wmin[a] = __reduce_min_sync(0xffffffffu, wmin[a]);
+        wmax[a] = __reduce_max_sync(0xffffffffu, wmax[a]);
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h) nmax[h][a] = __reduce_max_sync(0xffffffffu, nmax[h][a]);
+    }
+    if (lane == 0) {
+        ctl->wmin[0] = wmin[0]; ctl->wmin[1] = wmin[1];
+        ctl->wmax[0] = wmax[0]; ctl->wmax[1] = wmax[1];
+        for (int h = 0; h < kMaxHeads; ++h) { ctl->hd[h].nmax[0] = nmax[h][0]; ctl->hd[h].nmax[1] = nmax[h][1]; }
+        if (!fits) ctl->flags &= ~kRecFits;
+    }
+    __syncwarp();
+}
+
+// Cuts every pooled size's bins into chunks whose x footprints fit a span of kSW columns
+// (as build_chunks), one lane per bin: the end of a chunk is the first bin that no longer
+// fits, found with one ballot; its per-offset bin counts and column mask are reductions.
+__device__ __forceinline__ void warp_build_chunks(const KParams &P, const RoiCtx &c, BlockCtl *ctl, int max_bins,
+                                                  int lane)
+{
+    for (int h = 0; h < P.n_heads; ++h) {
+        const AxisTab &xt = ctl->hd[h].tab[1];
+        const int PW = P.PW[h];
+        const int W = c.L.W;
+        int NX = ctl->hd[h].nmax[1];
+        NX = NX < 1 ? 1 : NX;
+        const int lo_l = lane < PW ? xt.lo[lane] : 0;
+        const int n_l = lane < PW ? xt.n[lane] : 0;
+        int n = 0, pa = 0;
+        while (pa < PW) {
+            const int lo_a = __shfl_sync(0xffffffffu, lo_l, pa);
+            int x0 = lo_a < W - kSW ? lo_a : W - kSW;   // span [x0, x0 + kSW) inside the image
+            x0 = x0 < 0 ? 0 : x0;
+            const int last = lo_l + NX - 1;
+            const int lim = last < W - 1 ? last : W - 1;   // taps beyond the image carry no weight
+            const bool out = lane > pa && lane < PW && (lim - x0 >= kSW || lane - pa >= max_bins);
+            const unsigned mo = __ballot_sync(0xffffffffu, out);
+            const int pe = mo ? __ffs(mo) - 1 : PW;          // first bin of the next chunk
+            const bool in = lane >= pa && lane < pe;
+            // per-offset counts (one byte each): sum of 1 << 8 * (lo - x0) over the chunk's bins
+            const int sh8 = in ? 8 * (lo_l - x0) : 0;
+            unsigned c_lo = (in && sh8 < 32) ? (1u << sh8) : 0u;
+            unsigned c_hi = (in && sh8 >= 32) ? (1u << (sh8 - 32)) : 0u;
+            unsigned msk = in ? (((1u << n_l) - 1u) << (lo_l - x0)) : 0u;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                c_lo += __shfl_xor_sync(0xffffffffu, c_lo, d);
+                c_hi += __shfl_xor_sync(0xffffffffu, c_hi, d);
+            }
+            msk = __reduce_or_sync(0xffffffffu, msk);
+            if (lane == 0) {
+                ctl->hd[h].cstart[n] = (unsigned char)pa;
+                ctl->hd[h].cx0[n] = x0;
+                ctl->hd[h].ccnt[n] = ((unsigned long long)c_hi << 32) | c_lo;
+                ctl->hd[h].cmask[n] = (unsigned char)(msk & 0xffu);
+            }
+            ++n;
+            pa = pe;
+        }
+        if (lane == 0) {
+            ctl->hd[h].cstart[n] = (unsigned char)PW;
+            ctl->hd[h].nchunk = n;
+        }
+    }
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(kPlanThreads)
 rpool_plan_kernel(const __grid_constant__ KParams P, const __grid_constant__ PlanParams p,
                   unsigned char *recs_fwd, unsigned char *recs_bwd)
 {
-    __shared__ __align__(16) BlockCtl ctl_s;
-    __shared__ int s_sum[2];
+    __shared__ __align__(16) BlockCtl ctl_s[kPlanWarps];
     __shared__ int s_hist[kPlanMaxKeys + 1];
-    BlockCtl *ctl = &ctl_s;
-    const int tid = threadIdx.x;
-    const int i = blockIdx.x;
-    const bool first = (i == 0);          // this CTA also writes gstart
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x * kPlanWarps + warp;
+    const bool first = (blockIdx.x == 0);         // this CTA also writes gstart
 
-    int lvl, fl;
-    const int key = plan_key(p, i, lvl, fl);
-    int slot = i;
-    if (first)
-        for (int k = tid; k <= kPlanMaxKeys; k += kPlanThreads) s_hist[k] = 0;
-    if (first) __syncthreads();
-    if (p.order_mode != RPOOL_SCHED_INPUT) {
-        int acc = 0;
-        if (p.n_blocks == 0) {
-            for (int j = tid; j < p.R; j += kPlanThreads) {
-                int l2, f2;
-                const int kj = plan_key(p, j, l2, f2);
-                acc += (kj < key || (kj == key && j < i)) ? 1 : 0;
-                if (first) atomicAdd(&s_hist[kj], 1);
-            }
-        } else {
-            const int blk = i / kKeyBlock;
-            const int n = p.n_blocks * p.K;
-            for (int e = tid; e < n; e += kPlanThreads) {
-                const int b = e / p.K, k = e - b * p.K;
-                const int v = __ldg(p.bh + e);
-                acc += (k < key || (k == key && b < blk)) ? v : 0;
-                if (first) atomicAdd(&s_hist[k], v);
-            }
-            for (int j = blk * kKeyBlock + tid; j < i; j += kPlanThreads)
-                acc += (__ldg(p.keys + j) == key) ? 1 : 0;
-        }
-        slot = plan_cta_sum(acc, s_sum);
-    }
-    if (tid == 0) {
-        p.levels[i] = lvl;
-        p.order[slot] = i;
-        p.rflags[i] = fl;
-        if (first) *p.det_err = 0;
-    }
+    // ---- gstart: first slot of every key (CTA 0, all its warps)
     if (first && p.gstart) {
+        for (int k = tid; k <= kPlanMaxKeys; k += kPlanThreads) s_hist[k] = 0;
+        __syncthreads();
+        if (p.order_mode != RPOOL_SCHED_INPUT) {
+            if (p.n_blocks == 0) {
+                for (int j = tid; j < p.R; j += kPlanThreads) {
+                    int l2, f2;
+                    atomicAdd(&s_hist[plan_key(p, j, l2, f2)], 1);
+                }
+            } else {
+                const int n = p.n_blocks * p.K;
+                for (int e = tid; e < n; e += kPlanThreads) atomicAdd(&s_hist[e % p.K], __ldg(p.bh + e));
+            }
+        }
         __syncthreads();
         if (tid == 0) {
             const bool groups = p.by_image && p.order_mode == RPOOL_SCHED_DEFAULT;
@@ -951,10 +944,43 @@ rpool_plan_kernel(const __grid_constant__ KParams P, const __grid_constant__ Pla
                 p.gstart[k] = groups ? (k < p.K ? run : p.R) : -1;
                 run += t;
             }
+            *p.det_err = 0;
         }
+    }
+    if (i >= p.R) return;
+
+    // ---- slot of RoI i: stable rank of (key_i, i)
+    int lvl, fl;
+    const int key = plan_key(p, i, lvl, fl);
+    int slot = i;
+    if (p.order_mode != RPOOL_SCHED_INPUT) {
+        int acc = 0;
+        if (p.n_blocks == 0) {
+            for (int j = lane; j < p.R; j += 32) {
+                int l2, f2;
+                const int kj = plan_key(p, j, l2, f2);
+                acc += (kj < key || (kj == key && j < i)) ? 1 : 0;
+            }
+        } else {
+            const int blk = i / kKeyBlock;
+            const int n = p.n_blocks * p.K;
+            for (int e = lane; e < n; e += 32) {
+                const int b = e / p.K, k = e - b * p.K;
+                acc += (k < key || (k == key && b < blk)) ? __ldg(p.bh + e) : 0;
+            }
+            for (int j = blk * kKeyBlock + lane; j < i; j += 32)
+                acc += (__ldg(p.keys + j) == key) ? 1 : 0;
+        }
+        slot = __reduce_add_sync(0xffffffffu, acc);
+    }
+    if (lane == 0) {
+        p.levels[i] = lvl;
+        p.order[slot] = i;
+        p.rflags[i] = fl;
     }
 
     // ---- the RoI's record(s)
+    BlockCtl *ctl = &ctl_s[warp];
     RoiCtx c;
     c.r = i;
     c.lvl = lvl;
@@ -965,20 +991,20 @@ rpool_plan_kernel(const __grid_constant__ KParams P, const __grid_constant__ Pla
     c.fast_ok = shapes_allow_tables(P, c.L);
     const int n16 = rec_bytes(P.n_heads) >> 4;
     for (int bwd = 0; bwd < (recs_bwd != recs_fwd ? 2 : 1); ++bwd) {
-        __syncthreads();    // the previous set has left shared memory
-        if (tid == 0) {
+        __syncwarp();    // the previous set has left shared memory
+        if (lane == 0) {
             ctl->r = c.r; ctl->lvl = c.lvl; ctl->b = c.b;
             ctl->flags = (c.valid ? kRecValid : 0) | (c.fast_ok ? kRecShape : 0) | kRecFits;
         }
+        __syncwarp();
         if (c.valid && c.fast_ok) {      // (uniform) otherwise the consumer takes the generic path
-            build_tables(P, c, bwd != 0, ctl);
-            if (ctl->flags & kRecFits) build_chunks(P, c, ctl, kPMax);   // (uniform: read after the sync)
-        } else {
-            __syncthreads();
+            warp_build_tables(P, c, bwd != 0, ctl, lane);
+            if (ctl->flags & kRecFits) warp_build_chunks(P, c, ctl, kPMax, lane);
         }
+        __syncwarp();
         const uint4 *src = reinterpret_cast<const uint4 *>(ctl);
         uint4 *dst = reinterpret_cast<uint4 *>((bwd ? recs_bwd : recs_fwd) + (size_t)slot * P.rec_stride);
-        for (int k = tid; k < n16; k += kPlanThreads) dst[k] = src[k];
+        for (int k = lane; k < n16; k += 32) dst[k] = src[k];
     }
 }
 
