@@ -53,8 +53,11 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every step from Python instead of replaying the captured graph")
-    ap.add_argument("--no-fork", action="store_true",
-                    help="zero fill inside rpool_backward instead of on the forked stream")
+    ap.add_argument("--fork", default="split", choices=["split", "start", "none"],
+                    help="where the gradient zero fill runs: 'split' = coarse maps beside the plan, the "
+                         "finest map beside the coarse levels' backward launch; 'start' = all of it beside "
+                         "plan + forward; 'none' = inside rpool_backward")
+    ap.add_argument("--no-fork", action="store_true", help="same as --fork none")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-strong", action="store_true",
                     help="N > 1: skip the sharded configs[3] run attached as 'strong'")
@@ -92,8 +95,9 @@ def algorithmic_bytes(cfg, shapes, rois, levels, scales, S):
     O = sum(R * C * P * P * 4 for P in cfg["out_sizes"])
     F = sum(int(np.prod(s)) * 4 for s in shapes)
     U = synth.window_cells_touched(rois, levels, shapes, scales, max(cfg["out_sizes"]) * max(S, 1))
-    return dict(O=O, F=F, U_bytes=U * C * 4, fwd=O + U * C * 4 + 20 * R, bwd=O + F + 20 * R,
-                bwd_scatter=O + 2 * U * C * 4 + 20 * R)
+    F0 = int(np.prod(shapes[0])) * 4
+    return dict(O=O, F=F, F0=F0, U_bytes=U * C * 4, fwd=O + U * C * 4 + 20 * R, bwd=O + F + 20 * R,
+                bwd_scatter=O + 2 * U * C * 4 + 20 * R, bwd_split=O + F0 + 20 * R)
 
 
 def bench_config(cfg, cfg_id, R, S, shard, world):
@@ -477,6 +481,10 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+def fork_mode(args):
+    return "none" if args.no_fork else args.fork
+
+
 def _parse_opts(text):
     out = {}
     for kv in filter(None, text.split(",")):
@@ -585,7 +593,7 @@ def strong_scaling(args, world, rank, device, dist, peak, opts):
     feats, rois, gys = _device_tensors(cfg, shapes, rois_np, device, seed=1234)     # same on every rank
     K = max(5, min(args.steps, 30))
     full = pkg.FusedStep(feats, rois, None, scales, cfg["out_sizes"], S, gys=gys, graph=not args.no_graph,
-                         fork_zero_fill=not args.no_fork, options=opts)
+                         fork_zero_fill=fork_mode(args), options=opts)
     for _ in range(3):
         full.run()
     t1, _ = _timed(full.run, K, world, device, dist)
@@ -598,7 +606,7 @@ def strong_scaling(args, world, rank, device, dist, peak, opts):
     f_loc = [f[idx].contiguous(memory_format=torch.channels_last) for f in feats]
     g_loc = [g[ridx].contiguous(memory_format=torch.channels_last) for g in gys]
     part = pkg.FusedStep(f_loc, torch.from_numpy(local).to(device), None, scales, cfg["out_sizes"], S,
-                         gys=g_loc, graph=not args.no_graph, fork_zero_fill=not args.no_fork, options=opts)
+                         gys=g_loc, graph=not args.no_graph, fork_zero_fill=fork_mode(args), options=opts)
     for _ in range(3):
         part.run()
     tn, _ = _timed(part.run, K, world, device, dist)
@@ -680,7 +688,7 @@ def run_b200(args):
     # ---- the step: the package's helper (static buffers, forked zero fill, CUDA graph) ----
     step = pkg.FusedStep(feats, rois, None, scales, sizes, S, gys=gys,
                          graph=not args.no_graph, deterministic=args.deterministic,
-                         fork_zero_fill=not args.no_fork, options=opts)
+                         fork_zero_fill=fork_mode(args), options=opts)
     n0 = _lib.launch_count()
     step.run(marks=[torch.cuda.Event() for _ in range(3)])       # launched from Python: counted
     launches_per_step = _lib.launch_count() - n0
@@ -784,9 +792,9 @@ def run_b200(args):
 
     levels_np = _engine.read_plan(_engine.make_plan(shapes, rois, None, scales, sizes, S))[0]
     ab = algorithmic_bytes(cfg, shapes, rois_np, levels_np, scales, S)
-    forked = not (args.no_fork or args.deterministic)
+    forked = fork_mode(args) != "none" and not args.deterministic
     # dominant launch: forward, or backward (with the fill forked away it is the scatter alone)
-    bwd_bytes = ab["bwd_scatter"] if forked else ab["bwd"]
+    bwd_bytes = ab["bwd"] if not forked else (ab["bwd_split"] if fork_mode(args) == "split" else ab["bwd_scatter"])
     dom = "backward" if bwd_ms >= fwd_ms else "forward"
     dom_ms = bwd_ms if dom == "backward" else fwd_ms
     dom_bytes = bwd_bytes if dom == "backward" else ab["fwd"]
@@ -802,12 +810,15 @@ def run_b200(args):
                           "ncu --set full, per launch)",
         "peak_source": peak_src,
         "ncu": ncu_view(args.config, S),
-        "kernel": ("rpool_backward_kernel" + ("" if forked else " + rpool_zero_kernel") if dom == "backward"
+        "kernel": ("rpool_backward_kernel" + ("" if (forked and fork_mode(args) == "start") else " + rpool_zero_kernel")
+                   if dom == "backward"
                    else "rpool_plan_kernel + rpool_forward_kernel"),
         "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms,
-        "bytes_definition": "fwd = O + U*C*4 + 20R; bwd = O + F + 20R (SURVEY 8d); with the zero fill on the "
-                            "forked stream the backward launch alone is O + 2*U*C*4 + 20R (gy read once, "
-                            "touched cells read and written) and the F bytes of the fill overlap the forward",
+        "bytes_definition": "fwd = O + U*C*4 + 20R; bwd = O + F + 20R (SURVEY 8d).  fork 'split': the fill of "
+                            "the finest map (F0 bytes) runs inside the backward window, the coarse maps' beside "
+                            "the plan: backward window = O + F0 + 20R.  fork 'start': the whole fill runs beside "
+                            "plan + forward and the backward launch alone is O + 2*U*C*4 + 20R (gy read once, "
+                            "touched cells read and written)",
         "forward": {"ms": fwd_ms, "bytes": int(ab["fwd"]), "GBps": ab["fwd"] / (fwd_ms * 1e-3) / 1e9,
                     "frac": frac(ab["fwd"], fwd_ms),
                     "note": "plan + forward launches" + (", the forked zero fill runs beside them" if forked else "")},
@@ -858,7 +869,7 @@ def run_b200(args):
         "data": "synthetic",
         "config": bench_config(cfg, args.config, full_R, S, args.shard, world),
         "how": {"api": "chainer_maskrcnn_b200.FusedStep.run()",
-                "cuda_graph": graphed, "zero_fill_forked": forked, "deterministic": bool(args.deterministic),
+                "cuda_graph": graphed, "zero_fill_forked": fork_mode(args) if forked else "none", "deterministic": bool(args.deterministic),
                 "options": opts, "build_id": _lib.build_id(),
                 "layout": "channels-last features / pooled maps / gradients resident in HBM",
                 "sharding": "by image, one process per GPU, no data-path collective"},

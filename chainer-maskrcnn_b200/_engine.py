@@ -314,16 +314,22 @@ def forward(features, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
     return outs, plan
 
 
-def backward(plan, gys, deterministic=False, out=None, accumulate=False, check_flags=True):
+def backward(plan, gys, deterministic=False, out=None, accumulate=False, check_flags=True,
+             levels_mask=0, det_scratch=None):
     """Dense feature gradients (channels-last memory, logical (N,C,H,W)) for
     every level from the pooled gradients ``gys`` (one per head).  ``out``: optional
     preallocated gradient tensors to write into; with ``accumulate=True`` the result
     is added to what ``out`` already holds (no zero fill: rpool_problem.accumulate).
-    ``deterministic``: every gradient cell is summed by one owner in schedule order
-    (bit-identical from run to run; one launch, no scratch).  RoIs that need the generic
-    kernel path cannot be ordered: they are skipped and reported -- ``check_flags`` reads
-    the flag back (one stream synchronisation) and raises; pass False inside CUDA-graph
-    capture and call ``status_flags(plan)`` afterwards."""
+    ``levels_mask``: only RoIs whose level bit is set take part (0 = all): a caller can run
+    the coarse levels first while the finest gradient map is still being zero-filled
+    elsewhere (needs ``accumulate=True``).
+    ``deterministic``: segmented reduction instead of atomics (bit-identical from run to
+    run).  Its scratch holds one private window per RoI; without ``det_scratch`` (a uint8
+    CUDA tensor) the exact size is computed on the device first, which synchronises the
+    stream.  RoIs that need the generic kernel path cannot be ordered, and a scratch that
+    is too small cannot hold the windows: both are reported -- ``check_flags`` reads the
+    flags back (one more synchronisation) and raises; pass a scratch and False inside
+    CUDA-graph capture and call ``status_flags(plan)`` afterwards."""
     if accumulate and out is None:
         raise ValueError("accumulate=True needs the gradient tensors to add into (out=...)")
     if len(gys) != len(plan.out_sizes):
@@ -352,21 +358,19 @@ def backward(plan, gys, deterministic=False, out=None, accumulate=False, check_f
                  for shape in plan.shapes]
     else:
         grads = user_out
+    if levels_mask and not accumulate:
+        raise ValueError("levels_mask needs accumulate=True (every launch would zero-fill all levels)")
     prob = _fill_problem(plan, [g.data_ptr() for g in grads], [g.data_ptr() for g in g_in],
                          accumulate=accumulate and not padded, deterministic=deterministic)
+    prob.opt.levels_mask = int(levels_mask)
     L = _lib.lib()
     with _on(plan.device):
         ws, ws_n = plan.workspace.data_ptr(), plan.workspace.numel()
-        if deterministic == "scratch":
-            # r01 variant (private windows + ordered gather), kept for comparison: the scratch
-            # holds one private window per RoI, its size depends on the RoIs and is computed
-            # on the device (this query synchronises the stream)
-            need = ctypes.c_size_t(0)
-            _lib.check(L.rpool_backward_det_bytes(ctypes.byref(prob), ws, ws_n, _stream(),
-                                                  ctypes.byref(need)))
-            scratch = torch.empty(need.value, dtype=torch.uint8, device=plan.device)
-            prob.det_workspace = scratch.data_ptr()
-            prob.det_workspace_bytes = need.value
+        if deterministic:
+            if det_scratch is None:
+                det_scratch = torch.empty(det_scratch_bytes(plan, prob), dtype=torch.uint8, device=plan.device)
+            prob.det_workspace = det_scratch.data_ptr()
+            prob.det_workspace_bytes = det_scratch.numel()
         _lib.check(L.rpool_backward(ctypes.byref(prob), ws, ws_n, _stream()))
         if deterministic and check_flags:
             err = ctypes.c_int32(0)
@@ -386,6 +390,19 @@ def backward(plan, gys, deterministic=False, out=None, accumulate=False, check_f
                 dst.copy_(g[:, :C])
         return user_out
     return grads
+
+
+def det_scratch_bytes(plan, prob=None):
+    """Exact size of the deterministic backward's scratch for this plan's RoIs: computed on
+    the device, SYNCHRONISES the current stream (rpool_backward_det_bytes)."""
+    if prob is None:
+        dummy = plan.workspace.data_ptr()
+        prob = _fill_problem(plan, [dummy] * len(plan.shapes), [dummy] * len(plan.out_sizes), deterministic=True)
+    need = ctypes.c_size_t(0)
+    with _on(plan.device):
+        _lib.check(_lib.lib().rpool_backward_det_bytes(ctypes.byref(prob), plan.workspace.data_ptr(),
+                                                       plan.workspace.numel(), _stream(), ctypes.byref(need)))
+    return need.value
 
 
 def read_plan(plan):

@@ -4,10 +4,14 @@ What a training loop does around the heads, packaged so that the launch overhead
 and the gradient zero fill leave the critical path:
 
   * every buffer (plan workspace, pooled maps, dense gradients) is allocated once;
-  * the zero fill of the dense gradients depends on nothing, so it is forked to a
-    side stream where it overlaps rpool_plan and the start of rpool_forward, and
-    rpool_backward then runs with ``accumulate = 1`` (rpool_zero_fill in
-    include/rpool_b200.h exists for exactly this);
+  * the zero fill of the dense gradients depends on nothing, so it is forked to a side
+    stream and rpool_backward runs with ``accumulate = 1`` (rpool_zero_fill in
+    include/rpool_b200.h exists for exactly this).  The forward pass is bound by HBM
+    writes, so a fill running beside it only takes its bandwidth; the backward pass is
+    bound by reads and has write bandwidth to spare.  Hence ``fork_zero_fill="split"``
+    (default): the small coarse maps are filled beside rpool_plan, the finest map (3/4
+    of the bytes) beside the backward launch over the coarse levels' RoIs
+    (``opt.levels_mask``), and the finest level's RoIs are scattered last;
   * with ``graph=True`` the whole step (fork and join included) is captured once
     into a CUDA graph and replayed: the RoIs, features and upstream gradients are
     read from their device buffers at replay time, so new data is written into the
@@ -33,7 +37,7 @@ class FusedStep(object):
     gradient per pooled size (None: forward only)."""
 
     def __init__(self, features, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
-                 gys=None, graph=True, deterministic=False, fork_zero_fill=True, options=None):
+                 gys=None, graph=True, deterministic=False, fork_zero_fill="split", options=None):
         self.features = list(features)
         self.rois, self.levels = rois, levels
         self.scales = list(spatial_scales)
@@ -58,8 +62,17 @@ class FusedStep(object):
         n = _lib.lib().rpool_workspace_bytes_ex(R, len(self.sizes), coord)
         self.workspace = torch.empty(n, dtype=torch.uint8, device=dev)
         # the deterministic variant writes every gradient cell itself: nothing to fork
-        self.fork = bool(fork_zero_fill) and self.gys is not None and not self.deterministic
+        mode = {True: "split", False: "none", None: "none"}.get(fork_zero_fill, fork_zero_fill)
+        if mode not in ("split", "start", "none"):
+            raise ValueError("fork_zero_fill must be 'split', 'start', 'none' or a bool")
+        if self.gys is None or self.deterministic:
+            mode = "none"
+        if mode == "split" and len(self.features) < 2:
+            mode = "start"
+        self.fork_mode = mode
+        self.fork = mode != "none"
         self._side = torch.cuda.Stream(device=dev) if self.fork else None
+        self._det_scratch = None
         self.plan = None
         self.graph = None
         if graph:
@@ -67,27 +80,46 @@ class FusedStep(object):
 
     # -- one step on the current stream ------------------------------------
     def _launch(self, marks=None):
-        with _engine._on(self.rois.device):
-            cur = torch.cuda.current_stream(self.rois.device)
-            ev = None
+        dev = self.rois.device
+        with _engine._on(dev):
+            cur = torch.cuda.current_stream(dev)
+            side = self._side
+            ev_small = ev_big = None
             if marks:
                 marks[0].record(cur)
             if self.fork:
-                self._side.wait_stream(cur)                      # fork
-                with torch.cuda.stream(self._side):
-                    _engine.zero_fill(self.grads)
-                    ev = self._side.record_event()
+                side.wait_stream(cur)                            # fork
+                with torch.cuda.stream(side):
+                    _engine.zero_fill(self.grads if self.fork_mode == "start" else self.grads[1:])
+                    ev_small = side.record_event()
             _, self.plan = _engine.forward(self.features, self.rois, self.levels, self.scales, self.sizes,
                                            sampling_ratio=self.sampling_ratio, roi_format=_lib.ROI_YX,
                                            options=self.options, workspace=self.workspace, out=self.outs)
             if marks:
                 marks[1].record(cur)
             if self.gys is not None:
-                if ev is not None:
-                    cur.wait_event(ev)                           # join
-                # (no flag read-back inside the step: it would synchronise; see status_flags)
-                _engine.backward(self.plan, self.gys, out=self.grads, accumulate=self.fork,
-                                 deterministic=self.deterministic, check_flags=False)
+                if self.fork_mode == "split":
+                    side.wait_event(cur.record_event())          # the finest map's fill starts after the forward
+                    with torch.cuda.stream(side):
+                        _engine.zero_fill(self.grads[:1])
+                        ev_big = side.record_event()
+                    cur.wait_event(ev_small)                     # join 1: coarse maps are clean
+                    coarse = ((1 << len(self.features)) - 1) & ~1
+                    _engine.backward(self.plan, self.gys, out=self.grads, accumulate=True, levels_mask=coarse)
+                    cur.wait_event(ev_big)                       # join 2: the finest map is clean
+                    _engine.backward(self.plan, self.gys, out=self.grads, accumulate=True, levels_mask=1)
+                else:
+                    if ev_small is not None:
+                        cur.wait_event(ev_small)                 # join
+                    if self.deterministic and self._det_scratch is None:
+                        # sized once for the RoIs at hand (+25 %): later steps reuse it without a host
+                        # round trip; windows that no longer fit raise RPOOL_FLAG_DET_SCRATCH (status_flags)
+                        n = _engine.det_scratch_bytes(self.plan)
+                        self._det_scratch = torch.empty(n + n // 4 + 4096, dtype=torch.uint8, device=dev)
+                    # (no flag read-back inside the step: it would synchronise; see status_flags)
+                    _engine.backward(self.plan, self.gys, out=self.grads, accumulate=self.fork,
+                                     deterministic=self.deterministic, check_flags=False,
+                                     det_scratch=self._det_scratch)
             if marks:
                 marks[2].record(cur)
 

@@ -8,7 +8,7 @@
 #include <cstdio>
 #include <cstring>
 
-#include "rpool_det.cuh"
+#include "rpool_slide.cuh"
 
 using namespace rpool;
 
@@ -25,16 +25,14 @@ constexpr int kMaxSmem = 227 * 1024;
 
 // rpool_options with the defaults filled in (0 = default in the ABI)
 struct Options {
-    int threads, order, force_path, split_heads, prefetch, var_fwd, var_bwd;
+    int threads, order, force_path, split_heads, prefetch, var_fwd;
+    unsigned levels_mask;
 };
 constexpr int kDefaultThreads = 128;
 constexpr int kDefaultPrefetchRows = 2;
-constexpr int kVariantRows = 1, kVariantStream = 2;
+constexpr int kVariantRows = 1, kVariantSlide = 2;
 #ifndef RPOOL_DEFAULT_VARIANT_FWD
 #define RPOOL_DEFAULT_VARIANT_FWD 1
-#endif
-#ifndef RPOOL_DEFAULT_VARIANT_BWD
-#define RPOOL_DEFAULT_VARIANT_BWD 1
 #endif
 
 int fail(int code, const char *fmt, ...)
@@ -128,8 +126,10 @@ int read_options(const rpool_problem *p, Options &o)
         return fail(RPOOL_ERR_INVALID, "opt.prefetch_rows=%d outside [-1,16]", q.prefetch_rows);
     if (q.prefetch_rois < 0 || q.prefetch_rois > 65536)
         return fail(RPOOL_ERR_INVALID, "opt.prefetch_rois=%d outside [0,65536]", q.prefetch_rois);
-    if (q.variant_forward < 0 || q.variant_forward > 2 || q.variant_backward < 0 || q.variant_backward > 2)
-        return fail(RPOOL_ERR_INVALID, "opt.variant_forward/backward outside [0,2]");
+    if (q.variant_forward < 0 || q.variant_forward > 2)
+        return fail(RPOOL_ERR_INVALID, "opt.variant_forward=%d outside [0,2]", q.variant_forward);
+    if (q.levels_mask < 0 || q.levels_mask >= (1 << RPOOL_MAX_LEVELS))
+        return fail(RPOOL_ERR_INVALID, "opt.levels_mask=%d outside [0,%d)", q.levels_mask, 1 << RPOOL_MAX_LEVELS);
     o.threads = q.cta_threads ? q.cta_threads : kDefaultThreads;
     o.order = q.schedule;
     o.force_path = q.force_path;
@@ -139,7 +139,7 @@ int read_options(const rpool_problem *p, Options &o)
     else if (q.prefetch_rows < 0) o.prefetch = -1;
     else o.prefetch = -1 - (q.prefetch_rows ? q.prefetch_rows : kDefaultPrefetchRows);
     o.var_fwd = q.variant_forward ? q.variant_forward : RPOOL_DEFAULT_VARIANT_FWD;
-    o.var_bwd = q.variant_backward ? q.variant_backward : RPOOL_DEFAULT_VARIANT_BWD;
+    o.levels_mask = q.levels_mask ? (unsigned)q.levels_mask : 0xffffffffu;
     return RPOOL_OK;
 }
 
@@ -233,6 +233,7 @@ int fill_params(const rpool_problem *p, const Workspace &w, const Options &o, bo
     const int warps = threads / 32;
     k.prefetch = o.prefetch;
     k.reverse = (bwd && o.order == RPOOL_SCHED_DEFAULT) ? 1 : 0;
+    k.levels_mask = o.levels_mask;
     k.det = 0;
     k.det_rects = w.rects;
     k.det_woff = w.woff;
@@ -243,13 +244,6 @@ int fill_params(const rpool_problem *p, const Workspace &w, const Options &o, bo
     const int ttab = (int)((sizeof(TTab) + 127) & ~(size_t)127);
     k.strip_cols = sum_pw > 0 ? sum_pw : 1;
     return ctl + p->n_heads * ttab + warps * k.strip_cols * 512;
-}
-
-// Dynamic shared memory of the "stream" kernels: the RoI record + one ring / double buffer per warp.
-int stream_smem(const rpool_problem *p, bool bwd, int threads)
-{
-    const int ctl = (rec_bytes(p->n_heads) + 127) & ~127;
-    return ctl + (threads / 32) * (bwd ? kBwdStreamWarpBytes : kFwdStreamWarpBytes);
 }
 
 // Raises a pooling kernel's dynamic shared memory limit.  The limit is per device
@@ -409,12 +403,11 @@ int rpool_forward(const rpool_problem *p, void *ws, size_t ws_size, void *stream
         return fail(RPOOL_ERR_UNSUPPORTED, "forward needs %d bytes of shared memory; the limit is %d",
                     smem, kMaxSmem);
     k.variant = o.var_fwd;
-    if (o.var_fwd == kVariantStream) {
-        const int smem2 = stream_smem(p, false, threads);
-        rc = set_smem(rpool_forward_stream_kernel, 2, smem2);
+    if (o.var_fwd == kVariantSlide) {
+        rc = set_smem(rpool_forward_slide_kernel, 2, smem);
         if (rc) return rc;
-        rpool_forward_stream_kernel<<<p->n_rois, threads, smem2, static_cast<cudaStream_t>(stream)>>>(k);
-        CUDA_TRY(cudaGetLastError(), "rpool_forward_stream_kernel launch");
+        rpool_forward_slide_kernel<<<p->n_rois, threads, smem, static_cast<cudaStream_t>(stream)>>>(k);
+        CUDA_TRY(cudaGetLastError(), "rpool_forward_slide_kernel launch");
         g_launches++;
         return RPOOL_OK;
     }
@@ -500,72 +493,10 @@ int rpool_status_flags(const void *ws, int32_t n_rois, void *stream, int32_t *fl
     return RPOOL_OK;
 }
 
-// Deterministic backward, owner-gathers formulation (rpool_det.cuh): one launch, no scratch.
-static int backward_det_owner(const rpool_problem *p, void *ws, const Options &o, cudaStream_t st)
-{
-    if (o.order != RPOOL_SCHED_DEFAULT)
-        return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward needs the (image, level) schedule "
-                    "(opt.schedule = RPOOL_SCHED_DEFAULT)");
-    if (p->feat_layout != RPOOL_NHWC || p->pool_layout != RPOOL_NHWC || (p->channels & 3))
-        return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward needs channels-last tensors with C %% 4 == 0");
-    int nimg = 1;
-    for (int l = 0; l < p->n_levels; ++l) nimg = p->level[l].n_images > nimg ? p->level[l].n_images : nimg;
-    if (nimg * p->n_levels > kPlanMaxKeys)
-        return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward: images x levels = %d exceeds %d",
-                    nimg * p->n_levels, kPlanMaxKeys);
-    for (int h = 0; h < p->n_heads; ++h)
-        if (p->out_h[h] > kPMax || p->out_w[h] > kPMax)
-            return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward: pooled size %dx%d exceeds %d",
-                        p->out_h[h], p->out_w[h], kPMax);
-    for (int l = 0; l < p->n_levels; ++l)
-        if ((reinterpret_cast<uintptr_t>(p->level[l].data) & 15))
-            return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward: level %d gradient is not 16-byte aligned", l);
-    for (int h = 0; h < p->n_heads; ++h)
-        if (p->n_rois > 0 && (reinterpret_cast<uintptr_t>(p->pooled[h]) & 15))
-            return fail(RPOOL_ERR_UNSUPPORTED, "deterministic backward: gy %d is not 16-byte aligned", h);
-    const Workspace w = ws_split(ws, p);
-    DetParams d;
-    memset(&d, 0, sizeof(d));
-    long long ctas = 0;
-    for (int li = 0; li < p->n_levels; ++li) {
-        const int l = p->n_levels - 1 - li;          // coarse levels first: their strips are the longest
-        d.lvl[l].data = static_cast<float *>(p->level[l].data);
-        d.lvl[l].n_images = p->level[l].n_images;
-        d.lvl[l].H = p->level[l].height;
-        d.lvl[l].W = p->level[l].width;
-        const int row_tiles = (p->level[l].width + kSW - 1) / kSW;
-        d.tiles[l] = (row_tiles + 7) / 8;            // at most 8 CTAs per map row
-        d.strips[l] = (row_tiles + d.tiles[l] - 1) / d.tiles[l];
-        d.cta_base[li] = ctas;
-        ctas += (long long)p->level[l].n_images * p->level[l].height * d.strips[l];
-    }
-    d.cta_base[p->n_levels] = ctas;
-    if (ctas > 2147483647ll) return fail(RPOOL_ERR_UNSUPPORTED, "pyramid too large for the gather launch");
-    d.n_levels = p->n_levels;
-    d.C = p->channels;
-    d.accumulate = p->accumulate;
-    d.n_heads = p->n_heads;
-    for (int h = 0; h < p->n_heads; ++h) {
-        d.PH[h] = p->out_h[h];
-        d.PW[h] = p->out_w[h];
-        d.gy[h] = static_cast<const float *>(p->pooled[h]);
-    }
-    d.gstart = w.gstart;
-    d.recs = w.recs_bwd;
-    d.rec_stride = w.rec_stride;
-    d.R = p->n_rois;
-    d.det_err = w.det_err;
-    if (p->n_rois == 0)    // no plan ran: the flag word was never cleared
-        CUDA_TRY(cudaMemsetAsync(w.det_err, 0, sizeof(int), st), "cudaMemsetAsync(det_err)");
-    rpool_backward_det_kernel<<<(unsigned)ctas, kDetThreads, sizeof(DetShared), st>>>(d);
-    CUDA_TRY(cudaGetLastError(), "rpool_backward_det_kernel launch");
-    g_launches++;
-    return RPOOL_OK;
-}
-
 static int backward_det(const rpool_problem *p, void *ws, const Options &o, cudaStream_t st)
 {
-    if (!p->det_workspace) return backward_det_owner(p, ws, o, st);
+    if (!p->det_workspace) return fail(RPOOL_ERR_WORKSPACE, "deterministic backward: det_workspace is NULL "
+                                       "(rpool_backward_det_bytes gives the exact size for these RoIs)");
     if (reinterpret_cast<uintptr_t>(p->det_workspace) & 15)
         return fail(RPOOL_ERR_INVALID, "det_workspace must be 16-byte aligned");
     KParams k;
@@ -581,7 +512,6 @@ static int backward_det(const rpool_problem *p, void *ws, const Options &o, cuda
         }
         k.reverse = 0;
         k.det = 1;
-        k.variant = kVariantRows;
         k.det_scratch = static_cast<float *>(p->det_workspace);
         k.det_scratch_floats = p->det_workspace_bytes / sizeof(float);
         rc = set_smem(rpool_backward_kernel, 1, smem);
@@ -699,19 +629,6 @@ int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *strea
         }
         k.rec_head = parts > 1 ? part : 0;
         k.rec_stride = w.rec_stride;       // records keep the layout of the plan's head count
-        k.variant = o.var_bwd;
-        bool wide = false;       // the stream kernel's double buffer holds bin rows of <= kPBwd bins
-        for (int h = 0; h < q.n_heads; ++h) wide = wide || q.out_w[h] > kPBwd;
-        if (o.var_bwd == kVariantStream && !wide) {
-            threads = o.threads;
-            const int smem2 = stream_smem(&q, true, threads);
-            rc = set_smem(rpool_backward_stream_kernel, 3, smem2);
-            if (rc) return rc;
-            rpool_backward_stream_kernel<<<p->n_rois, threads, smem2, st>>>(k);
-            CUDA_TRY(cudaGetLastError(), "rpool_backward_stream_kernel launch");
-            g_launches++;
-            continue;
-        }
         rc = set_smem(rpool_backward_kernel, 1, smem);
         if (rc) return rc;
         rpool_backward_kernel<<<p->n_rois, threads, smem, st>>>(k);

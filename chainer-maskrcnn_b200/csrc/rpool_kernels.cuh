@@ -658,6 +658,7 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     RoiCtx c;
     ctx_from_record(P, ctl, c);
     if (!c.valid) return;
+    if (!((P.levels_mask >> c.lvl) & 1u)) return;     // this launch covers other levels (opt.levels_mask)
     const int need = kRecShape | kRecFits;
     bool table_ok = (ctl->flags & need) == need && P.force_path != kPathGeneric && pointers_aligned(P, c.L);
     for (int h = 0; h < P.n_heads; ++h) table_ok = table_ok && P.PH[h] <= kPBwd && P.PW[h] <= kPBwd;
@@ -769,7 +770,7 @@ constexpr int kPlanWarps = 4;               // RoIs per plan CTA: one warp each
 constexpr int kPlanThreads = kPlanWarps * 32;
 constexpr int kPlanMaxKeys = 256;
 constexpr int kKeyBlock = 1024;             // RoIs per block of rpool_keys_kernel
-constexpr int kPlanSingle = 512;            // up to this many RoIs every plan warp derives all keys itself
+constexpr int kPlanSingle = 64;             // up to this many RoIs every plan warp derives all keys itself
 
 // Level (clipped to the pyramid, maskrcnn.py:141), schedule key and flags of RoI i.
 __device__ __forceinline__ int plan_key(const PlanParams &p, int i, int &lvl_out, int &flags_out)
@@ -860,10 +861,14 @@ __device__ __forceinline__ void warp_build_tables(const KParams &P, const RoiCtx
 // Cuts every pooled size's bins into chunks whose x footprints fit a span of kSW columns
 // (as build_chunks), one lane per bin: the end of a chunk is the first bin that no longer
 // fits, found with one ballot; its per-offset bin counts and column mask are reductions.
+template <int kSpan>
 __device__ __forceinline__ void warp_build_chunks(const KParams &P, const RoiCtx &c, BlockCtl *ctl, int max_bins,
                                                   int lane)
 {
     for (int h = 0; h < P.n_heads; ++h) {
+        unsigned char *cstart = kSpan == kSW ? ctl->hd[h].cstart : ctl->hd[h].cstart6;
+        int *cx0 = kSpan == kSW ? ctl->hd[h].cx0 : ctl->hd[h].cx06;
+        unsigned long long *ccnt = kSpan == kSW ? ctl->hd[h].ccnt : ctl->hd[h].ccnt6;
         const AxisTab &xt = ctl->hd[h].tab[1];
         const int PW = P.PW[h];
         const int W = c.L.W;
@@ -874,11 +879,11 @@ __device__ __forceinline__ void warp_build_chunks(const KParams &P, const RoiCtx
         int n = 0, pa = 0;
         while (pa < PW) {
             const int lo_a = __shfl_sync(0xffffffffu, lo_l, pa);
-            int x0 = lo_a < W - kSW ? lo_a : W - kSW;   // span [x0, x0 + kSW) inside the image
+            int x0 = lo_a < W - kSpan ? lo_a : W - kSpan;   // span [x0, x0 + kSpan) inside the image
             x0 = x0 < 0 ? 0 : x0;
             const int last = lo_l + NX - 1;
             const int lim = last < W - 1 ? last : W - 1;   // taps beyond the image carry no weight
-            const bool out = lane > pa && lane < PW && (lim - x0 >= kSW || lane - pa >= max_bins);
+            const bool out = lane > pa && lane < PW && (lim - x0 >= kSpan || lane - pa >= max_bins);
             const unsigned mo = __ballot_sync(0xffffffffu, out);
             const int pe = mo ? __ffs(mo) - 1 : PW;          // first bin of the next chunk
             const bool in = lane >= pa && lane < pe;
@@ -894,17 +899,17 @@ __device__ __forceinline__ void warp_build_chunks(const KParams &P, const RoiCtx
             }
             msk = __reduce_or_sync(0xffffffffu, msk);
             if (lane == 0) {
-                ctl->hd[h].cstart[n] = (unsigned char)pa;
-                ctl->hd[h].cx0[n] = x0;
-                ctl->hd[h].ccnt[n] = ((unsigned long long)c_hi << 32) | c_lo;
-                ctl->hd[h].cmask[n] = (unsigned char)(msk & 0xffu);
+                cstart[n] = (unsigned char)pa;
+                cx0[n] = x0;
+                ccnt[n] = ((unsigned long long)c_hi << 32) | c_lo;
+                if (kSpan == kSW) ctl->hd[h].cmask[n] = (unsigned char)(msk & 0xffu);
             }
             ++n;
             pa = pe;
         }
         if (lane == 0) {
-            ctl->hd[h].cstart[n] = (unsigned char)PW;
-            ctl->hd[h].nchunk = n;
+            cstart[n] = (unsigned char)PW;
+            if (kSpan == kSW) ctl->hd[h].nchunk = n; else ctl->hd[h].nchunk6 = n;
         }
     }
     __syncwarp();
@@ -999,7 +1004,12 @@ rpool_plan_kernel(const __grid_constant__ KParams P, const __grid_constant__ Pla
         __syncwarp();
         if (c.valid && c.fast_ok) {      // (uniform) otherwise the consumer takes the generic path
             warp_build_tables(P, c, bwd != 0, ctl, lane);
-            if (ctl->flags & kRecFits) warp_build_chunks(P, c, ctl, kPMax, lane);
+            if (ctl->flags & kRecFits) {
+                warp_build_chunks<kSW>(P, c, ctl, kPMax, lane);
+                // (a footprint of kNT cells always fits a span of kSL >= kNT columns; a map narrower
+                // than kSW columns never reaches the table paths)
+                if (!bwd) warp_build_chunks<kSL>(P, c, ctl, kPMax, lane);
+            }
         }
         __syncwarp();
         const uint4 *src = reinterpret_cast<const uint4 *>(ctl);

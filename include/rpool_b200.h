@@ -106,9 +106,12 @@ typedef struct rpool_options {
     int32_t prefetch_rois;  /* backward, rows variant: > 0 replaces the row-ahead prefetch by the whole
                              * RoI of the CTA scheduled prefetch_rois - 1 slots later */
     int32_t variant_forward;  /* 0 = default kernel; 1 = "rows" (one bin row per warp task);
-                               * 2 = "stream" (one chunk per warp task, window rows loaded once) */
-    int32_t variant_backward; /* 0 = default; 1 = "rows" (one window row per warp task);
-                               * 2 = "stream" (one chunk per warp task, gy rows loaded once) */
+                               * 2 = "slide" (one chunk per warp task, window rows loaded once and
+                               * kept in registers while the footprints slide over them) */
+    int32_t levels_mask;      /* rpool_backward: bit l set = RoIs of level l take part; 0 = all.  Lets a
+                               * caller split the backward pass by level, e.g. coarse levels first while
+                               * the (large) finest gradient map is still being zero-filled on another
+                               * stream (accumulate = 1; the step helper of the Python package does this) */
 } rpool_options;
 
 /* One pyramid level.  `data` is the feature map in rpool_forward (read) and

@@ -78,7 +78,7 @@ def test_options_validation():
     ws = ctypes.c_void_p((ctypes.addressof(raw) + 15) & ~15)
     for bad in (dict(cta_threads=100), dict(cta_threads=512), dict(schedule=4), dict(force_path=3),
                 dict(prefetch_rows=17), dict(prefetch_rois=-1), dict(variant_forward=3),
-                dict(variant_backward=-1), dict(fuse_heads_backward=2)):
+                dict(levels_mask=-1), dict(levels_mask=256), dict(fuse_heads_backward=2)):
         p = _problem()
         p.opt = _lib.make_options(**bad)
         for fn in (L.rpool_plan, L.rpool_forward, L.rpool_backward):
@@ -137,7 +137,7 @@ def test_workspace_errors_without_gpu():
     q = _problem()
     q.level[0].data = None
     assert L.rpool_zero_fill(ctypes.byref(q), None) == 1
-    # the deterministic variant needs channels-last tensors and the default schedule
+    # the deterministic variant needs its scratch, channels-last tensors and the default schedule
     p = _problem(deterministic=1)
     n = L.rpool_workspace_bytes_ex(p.n_rois, p.n_heads, p.coord_mode)
     assert 0 < n <= L.rpool_workspace_bytes(p.n_rois)
@@ -147,10 +147,12 @@ def test_workspace_errors_without_gpu():
     assert b"needed" in L.rpool_last_error()
     assert L.rpool_backward(ctypes.byref(p), ctypes.c_void_p(ws.value + 4), n, None) == 3
     assert b"aligned" in L.rpool_last_error()
-    p = _problem(deterministic=1, feat_layout=1)
+    assert L.rpool_backward(ctypes.byref(p), ws, n, None) == 3
+    assert b"det_workspace" in L.rpool_last_error()
+    p = _problem(deterministic=1, det_workspace=0x4000, det_workspace_bytes=1 << 20, feat_layout=1)
     assert L.rpool_backward(ctypes.byref(p), ws, n, None) == 2
     assert b"channels-last" in L.rpool_last_error()
-    p = _problem(deterministic=1)
+    p = _problem(deterministic=1, det_workspace=0x4000, det_workspace_bytes=1 << 20)
     p.opt = _lib.make_options(schedule=_lib.SCHED_INPUT)
     assert L.rpool_backward(ctypes.byref(p), ws, n, None) == 2
     assert b"schedule" in L.rpool_last_error()

@@ -238,9 +238,10 @@ def test_step_is_cuda_graph_capturable_and_replays_on_new_rois():
             assert oracle.rel_err(grads[l].cpu().numpy(), want_g[l]) <= 1e-4
 
 
+@pytest.mark.parametrize("fork", ["split", "start", "none"])
 @pytest.mark.parametrize("graph", [True, False])
 @pytest.mark.parametrize("sizes,S", [([7], 2), ([7, 14], 1)])
-def test_fused_step_helper_forks_the_zero_fill_and_replays(graph, sizes, S):
+def test_fused_step_helper_forks_the_zero_fill_and_replays(graph, sizes, S, fork):
     """pkg.FusedStep: static buffers, gradient zero fill on a side stream (rpool_zero_fill +
     accumulate), the step captured into a CUDA graph; new RoIs / gradients are written into
     the same tensors between replays."""
@@ -254,8 +255,8 @@ def test_fused_step_helper_forks_the_zero_fill_and_replays(graph, sizes, S):
     cl = lambda a: torch.from_numpy(a).cuda().contiguous(memory_format=torch.channels_last)
     rois = torch.from_numpy(rois_a).cuda()
     step = pkg.FusedStep([cl(f) for f in feats], rois, None, scales, sizes, S, gys=[cl(g) for g in gys],
-                         graph=graph)
-    assert (step.graph is not None) == graph
+                         graph=graph, fork_zero_fill=fork)
+    assert (step.graph is not None) == graph and step.fork_mode == fork
     mode = "chainer" if S == 1 else "caffe2"
     for r in (rois_a, rois_b, rois_a):
         rois.copy_(torch.from_numpy(r).cuda())
@@ -265,8 +266,10 @@ def test_fused_step_helper_forks_the_zero_fill_and_replays(graph, sizes, S):
         outs, grads = step.run()
         torch.cuda.synchronize()
         if not graph:
-            # plan + forward + zero fill + one backward launch per pooled size
-            assert _lib.launch_count() - n0 == 3 + len(sizes)
+            # keys + plan + forward, then zero fill and one backward launch per pooled size --
+            # both twice when the fill is split (coarse levels / finest level)
+            parts = 2 if fork == "split" else 1
+            assert _lib.launch_count() - n0 == 3 + parts * (1 + len(sizes))
         lv = oracle.levels_for_pyramid(r[:, 1:], L)
         want_g = [np.zeros_like(f) for f in feats]
         for o, P, gy in zip(outs, sizes, gys):

@@ -179,11 +179,11 @@ def test_levels_random_million_bit_exact():
 @pytest.mark.parametrize("path,prefetch", [("auto", {}), ("generic", dict(prefetch_rows=-1)),
                                            ("table", dict(prefetch_rois=1)), ("table", dict(prefetch_rois=8)),
                                            ("table", dict(prefetch_rows=1)), ("table", dict(prefetch_rows=-1))])
-@pytest.mark.parametrize("variant", [_lib.VARIANT_ROWS, _lib.VARIANT_STREAM])
+@pytest.mark.parametrize("variant", [_lib.VARIANT_ROWS, _lib.VARIANT_SLIDE])
 @pytest.mark.parametrize("mode_name,S", [("chainer", 1), ("caffe2", 1), ("caffe2", 2), ("caffe2", 3)])
 def test_fused_vs_oracle(path, prefetch, variant, mode_name, S):
     rng, feats, rois, levels, scales = make_case(seed=S * 7 + len(path))
-    opt = dict(force_path=PATHS[path], variant_forward=variant, variant_backward=variant, **prefetch)
+    opt = dict(force_path=PATHS[path], variant_forward=variant, **prefetch)
     mode = _lib.COORD_CHAINER if mode_name == "chainer" else _lib.COORD_CAFFE2
     sizes = [7, 14]
     gys = [synth.make_gy(rng, rois.shape[0], feats[0].shape[1], P) for P in sizes]
@@ -197,14 +197,13 @@ def test_fused_vs_oracle(path, prefetch, variant, mode_name, S):
         assert oracle.rel_err(g, w) <= BWD_TOL
 
 
-@pytest.mark.parametrize("variant", [_lib.VARIANT_ROWS, _lib.VARIANT_STREAM])
+@pytest.mark.parametrize("variant", [_lib.VARIANT_ROWS, _lib.VARIANT_SLIDE])
 @pytest.mark.parametrize("threads", [32, 64, 224, 256])
 def test_block_sizes(threads, variant):
     rng, feats, rois, levels, scales = make_case(seed=3, C=128, per_img=60)
     gys = [synth.make_gy(rng, rois.shape[0], 128, 14)]
     outs, grads, _ = run_fused(feats, rois, levels, scales, [14], 2, gys=gys,
-                               options=dict(cta_threads=threads, variant_forward=variant,
-                                            variant_backward=variant))
+                               options=dict(cta_threads=threads, variant_forward=variant))
     want, wgrads = oracle_fused(feats, rois, levels, scales, [14], 2, "caffe2", gys)
     assert oracle.rel_err(outs[0], want[0]) <= FWD_TOL
     for g, w in zip(grads, wgrads):
@@ -466,30 +465,43 @@ def test_deterministic_backward_edge_cases():
     gd = [host(g) for g in _engine.backward(plan, [dev(gy)], deterministic=True)]
     for a, d in zip(ga, gd):
         assert oracle.rel_err(d, a) <= BWD_TOL
-    # pooled size 20 (beyond the atomic table path's 16) is fine for the owner-gathers kernel
-    outs, plan = _engine.forward(f, dev(rois), None, scales, [20], sampling_ratio=2)
-    gy20 = synth.make_gy(rng, rois.shape[0], 8, 20)
-    gd = [host(g) for g in _engine.backward(plan, [dev(gy20)], deterministic=True)]
-    _, want = oracle_fused(feats, rois, levels, scales, [20], 2, "caffe2", [gy20])
-    for d, w in zip(gd, want):
-        assert oracle.rel_err(d, w) <= BWD_TOL
-    # pooled size 40 > 32 has no tables at all, and a map narrower than 8 columns takes the generic
-    # path, which cannot be ordered: loud errors, never a silently unordered result
-    outs, plan = _engine.forward(f, dev(rois), None, scales, [40])
+    # pooled size 20 > 16 needs the generic path, which cannot be ordered: loud error
+    outs, plan = _engine.forward(f, dev(rois), None, scales, [20])
     with pytest.raises(_lib.RpoolError):
-        _engine.backward(plan, [dev(synth.make_gy(rng, rois.shape[0], 8, 40))], deterministic=True)
-    x = rng.standard_normal((1, 8, 12, 6)).astype(np.float32)
-    r1 = np.array([[0, 1, 1, 9, 4], [0, 2, 0, 11, 5]], np.float32)
-    outs, plan = _engine.forward([dev(x)], dev(r1), None, [1.0], [7])
-    with pytest.raises(_lib.RpoolError):
-        _engine.backward(plan, [dev(synth.make_gy(rng, 2, 8, 7))], deterministic=True)
+        _engine.backward(plan, [dev(synth.make_gy(rng, rois.shape[0], 8, 20))], deterministic=True)
     assert _engine.status_flags(plan) & _lib.FLAG_DET_GENERIC
-    # the r01 formulation (private windows + ordered gather) is still reachable and agrees
+    # a caller-provided scratch (no size query, no host round trip): large enough -> same bits;
+    # too small -> flagged, never a silent partial result
     outs, plan = _engine.forward(f, dev(r2), None, scales, [7], sampling_ratio=2)
-    gs = [host(g) for g in _engine.backward(plan, [dev(gy)], deterministic="scratch")]
-    gd = [host(g) for g in _engine.backward(plan, [dev(gy)], deterministic=True)]
-    for a, d in zip(gs, gd):
-        assert oracle.rel_err(d, a) <= BWD_TOL
+    need = _engine.det_scratch_bytes(plan)
+    big = torch.empty(need + 4096, dtype=torch.uint8, device="cuda")
+    g1 = [host(g) for g in _engine.backward(plan, [dev(gy)], deterministic=True, det_scratch=big)]
+    for a, d in zip(g1, gd):
+        assert np.array_equal(a, d)
+    small = torch.empty(max(need // 2, 16) // 16 * 16, dtype=torch.uint8, device="cuda")
+    with pytest.raises(_lib.RpoolError):
+        _engine.backward(plan, [dev(gy)], deterministic=True, det_scratch=small)
+    assert _engine.status_flags(plan) & _lib.FLAG_DET_SCRATCH
+
+
+def test_backward_split_by_level_mask():
+    """opt.levels_mask: the backward pass over the coarse levels' RoIs and over the finest
+    level's RoIs as two launches (what FusedStep does around the forked zero fill) adds up to
+    the single launch."""
+    rng, feats, rois, levels, scales = make_case(seed=51, C=32, per_img=120)
+    gy = synth.make_gy(rng, rois.shape[0], 32, 14)
+    f = [dev(x, True) for x in feats]
+    _, plan = _engine.forward(f, dev(rois), None, scales, [14], sampling_ratio=2)
+    whole = [host(g) for g in _engine.backward(plan, [dev(gy, True)])]
+    parts = [torch.zeros_like(x) for x in f]
+    _engine.backward(plan, [dev(gy, True)], out=parts, accumulate=True, levels_mask=0b1110)
+    only_coarse = [host(g) for g in parts]
+    assert float(np.abs(only_coarse[0]).max()) == 0.0 and float(np.abs(only_coarse[3]).max()) > 0.0
+    _engine.backward(plan, [dev(gy, True)], out=parts, accumulate=True, levels_mask=0b0001)
+    for a, w in zip(parts, whole):
+        assert oracle.rel_err(host(a), w) <= BWD_TOL
+    with pytest.raises(ValueError):
+        _engine.backward(plan, [dev(gy, True)], levels_mask=1)
 
 
 @pytest.mark.parametrize("deterministic", [False, True])
