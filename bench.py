@@ -53,9 +53,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every step from Python instead of replaying the captured graph")
-    ap.add_argument("--fork", default="split", choices=["split", "start", "none"],
-                    help="where the gradient zero fill runs: 'split' = coarse maps beside the plan, the "
-                         "finest map beside the coarse levels' backward launch; 'start' = all of it beside "
+    ap.add_argument("--fork", default="plan", choices=["plan", "start", "none"],
+                    help="where the gradient zero fill runs: 'plan' = what fits beside rpool_plan on a side "
+                         "stream, the rest right before the backward launch; 'start' = all of it beside "
                          "plan + forward; 'none' = inside rpool_backward")
     ap.add_argument("--no-fork", action="store_true", help="same as --fork none")
     ap.add_argument("--no-parity", action="store_true")
@@ -689,6 +689,7 @@ def run_b200(args):
     step = pkg.FusedStep(feats, rois, None, scales, sizes, S, gys=gys,
                          graph=not args.no_graph, deterministic=args.deterministic,
                          fork_zero_fill=fork_mode(args), options=opts)
+    late = sum(u.numel() * 4 for u in step._fill_late)     # bytes of the fill left inside the backward window
     n0 = _lib.launch_count()
     step.run(marks=[torch.cuda.Event() for _ in range(3)])       # launched from Python: counted
     launches_per_step = _lib.launch_count() - n0
@@ -794,7 +795,8 @@ def run_b200(args):
     ab = algorithmic_bytes(cfg, shapes, rois_np, levels_np, scales, S)
     forked = fork_mode(args) != "none" and not args.deterministic
     # dominant launch: forward, or backward (with the fill forked away it is the scatter alone)
-    bwd_bytes = ab["bwd"] if not forked else (ab["bwd_split"] if fork_mode(args) == "split" else ab["bwd_scatter"])
+    # the backward window (forward launch done -> backward launch done) holds the late part of the fill
+    bwd_bytes = ab["bwd"] if not forked else ab["bwd_scatter"] + late
     dom = "backward" if bwd_ms >= fwd_ms else "forward"
     dom_ms = bwd_ms if dom == "backward" else fwd_ms
     dom_bytes = bwd_bytes if dom == "backward" else ab["fwd"]
@@ -810,15 +812,13 @@ def run_b200(args):
                           "ncu --set full, per launch)",
         "peak_source": peak_src,
         "ncu": ncu_view(args.config, S),
-        "kernel": ("rpool_backward_kernel" + ("" if (forked and fork_mode(args) == "start") else " + rpool_zero_kernel")
+        "kernel": ("rpool_backward_kernel" + ("" if (forked and not late) else " + rpool_zero_kernel")
                    if dom == "backward"
                    else "rpool_plan_kernel + rpool_forward_kernel"),
         "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms,
-        "bytes_definition": "fwd = O + U*C*4 + 20R; bwd = O + F + 20R (SURVEY 8d).  fork 'split': the fill of "
-                            "the finest map (F0 bytes) runs inside the backward window, the coarse maps' beside "
-                            "the plan: backward window = O + F0 + 20R.  fork 'start': the whole fill runs beside "
-                            "plan + forward and the backward launch alone is O + 2*U*C*4 + 20R (gy read once, "
-                            "touched cells read and written)",
+        "bytes_definition": "fwd = O + U*C*4 + 20R; bwd = O + F + 20R (SURVEY 8d).  With part of the fill on the "
+                            "forked stream the backward window is O + 2*U*C*4 + 20R (gy read once, touched cells "
+                            "read and written) + the bytes of the fill that still runs inside it",
         "forward": {"ms": fwd_ms, "bytes": int(ab["fwd"]), "GBps": ab["fwd"] / (fwd_ms * 1e-3) / 1e9,
                     "frac": frac(ab["fwd"], fwd_ms),
                     "note": "plan + forward launches" + (", the forked zero fill runs beside them" if forked else "")},

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "librpool_b200.so")
 SOURCES = ["rpool_api.cu"]
-HEADERS = ["rpool_device.cuh", "rpool_kernels.cuh", "rpool_slide.cuh",
+HEADERS = ["rpool_device.cuh", "rpool_kernels.cuh", 
            os.path.join("..", "..", "include", "rpool_b200.h")]
 
 NVCC_FLAGS = [

@@ -315,14 +315,11 @@ def forward(features, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
 
 
 def backward(plan, gys, deterministic=False, out=None, accumulate=False, check_flags=True,
-             levels_mask=0, det_scratch=None):
+             det_scratch=None):
     """Dense feature gradients (channels-last memory, logical (N,C,H,W)) for
     every level from the pooled gradients ``gys`` (one per head).  ``out``: optional
     preallocated gradient tensors to write into; with ``accumulate=True`` the result
     is added to what ``out`` already holds (no zero fill: rpool_problem.accumulate).
-    ``levels_mask``: only RoIs whose level bit is set take part (0 = all): a caller can run
-    the coarse levels first while the finest gradient map is still being zero-filled
-    elsewhere (needs ``accumulate=True``).
     ``deterministic``: segmented reduction instead of atomics (bit-identical from run to
     run).  Its scratch holds one private window per RoI; without ``det_scratch`` (a uint8
     CUDA tensor) the exact size is computed on the device first, which synchronises the
@@ -358,11 +355,8 @@ def backward(plan, gys, deterministic=False, out=None, accumulate=False, check_f
                  for shape in plan.shapes]
     else:
         grads = user_out
-    if levels_mask and not accumulate:
-        raise ValueError("levels_mask needs accumulate=True (every launch would zero-fill all levels)")
     prob = _fill_problem(plan, [g.data_ptr() for g in grads], [g.data_ptr() for g in g_in],
                          accumulate=accumulate and not padded, deterministic=deterministic)
-    prob.opt.levels_mask = int(levels_mask)
     L = _lib.lib()
     with _on(plan.device):
         ws, ws_n = plan.workspace.data_ptr(), plan.workspace.numel()

@@ -19,7 +19,6 @@ COORD_CHAINER, COORD_CAFFE2 = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_TABLE = 0, 1, 2
 
 SCHED_DEFAULT, SCHED_INPUT, SCHED_LEVEL_DESC, SCHED_COARSE_FIRST = 0, 1, 2, 3
-VARIANT_DEFAULT, VARIANT_ROWS, VARIANT_SLIDE = 0, 1, 2
 FLAG_BAD_BATCH, FLAG_LEVEL_CLIPPED, FLAG_DET_GENERIC, FLAG_DET_SCRATCH = 1, 2, 4, 8
 
 UNSUPPORTED = 2
@@ -48,11 +47,10 @@ class Options(ctypes.Structure):
                 ("fuse_heads_backward", ctypes.c_int32),
                 ("prefetch_rows", ctypes.c_int32),
                 ("prefetch_rois", ctypes.c_int32),
-                ("variant_forward", ctypes.c_int32),
-                ("levels_mask", ctypes.c_int32)]
+                ("reserved", ctypes.c_int32 * 2)]
 
 
-OPTION_NAMES = tuple(n for n, _ in Options._fields_)
+OPTION_NAMES = tuple(n for n, _ in Options._fields_ if n != "reserved")
 
 
 class Problem(ctypes.Structure):

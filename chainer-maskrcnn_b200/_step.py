@@ -4,14 +4,16 @@ What a training loop does around the heads, packaged so that the launch overhead
 and the gradient zero fill leave the critical path:
 
   * every buffer (plan workspace, pooled maps, dense gradients) is allocated once;
-  * the zero fill of the dense gradients depends on nothing, so it is forked to a side
-    stream and rpool_backward runs with ``accumulate = 1`` (rpool_zero_fill in
-    include/rpool_b200.h exists for exactly this).  The forward pass is bound by HBM
-    writes, so a fill running beside it only takes its bandwidth; the backward pass is
-    bound by reads and has write bandwidth to spare.  Hence ``fork_zero_fill="split"``
-    (default): the small coarse maps are filled beside rpool_plan, the finest map (3/4
-    of the bytes) beside the backward launch over the coarse levels' RoIs
-    (``opt.levels_mask``), and the finest level's RoIs are scattered last;
+  * the zero fill of the dense gradients depends on nothing, so part of it is forked to
+    a side stream and rpool_backward runs with ``accumulate = 1`` (rpool_zero_fill in
+    include/rpool_b200.h exists for exactly this).  Which part: rpool_plan moves almost
+    no bytes, so a fill beside it is free, whereas the forward pass is bound by HBM
+    writes and a fill beside it only takes its bandwidth (measured: a fill forked
+    beside plan + forward makes the forward launch 30 us slower and the step no
+    faster).  ``fork_zero_fill="plan"`` (default) therefore fills, on the side stream,
+    as many (level, image) maps as fit in the plan's shadow, coarse levels first, and
+    the rest on the main stream right before the backward launch; ``"start"`` forks
+    the whole fill, ``"none"`` leaves it inside rpool_backward;
   * with ``graph=True`` the whole step (fork and join included) is captured once
     into a CUDA graph and replayed: the RoIs, features and upstream gradients are
     read from their device buffers at replay time, so new data is written into the
@@ -37,7 +39,7 @@ class FusedStep(object):
     gradient per pooled size (None: forward only)."""
 
     def __init__(self, features, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
-                 gys=None, graph=True, deterministic=False, fork_zero_fill="split", options=None):
+                 gys=None, graph=True, deterministic=False, fork_zero_fill="plan", options=None):
         self.features = list(features)
         self.rois, self.levels = rois, levels
         self.scales = list(spatial_scales)
@@ -62,64 +64,86 @@ class FusedStep(object):
         n = _lib.lib().rpool_workspace_bytes_ex(R, len(self.sizes), coord)
         self.workspace = torch.empty(n, dtype=torch.uint8, device=dev)
         # the deterministic variant writes every gradient cell itself: nothing to fork
-        mode = {True: "split", False: "none", None: "none"}.get(fork_zero_fill, fork_zero_fill)
-        if mode not in ("split", "start", "none"):
-            raise ValueError("fork_zero_fill must be 'split', 'start', 'none' or a bool")
+        mode = {True: "plan", False: "none", None: "none"}.get(fork_zero_fill, fork_zero_fill)
+        if mode not in ("plan", "start", "none"):
+            raise ValueError("fork_zero_fill must be 'plan', 'start', 'none' or a bool")
         if self.gys is None or self.deterministic:
             mode = "none"
-        if mode == "split" and len(self.features) < 2:
-            mode = "start"
         self.fork_mode = mode
         self.fork = mode != "none"
         self._side = torch.cuda.Stream(device=dev) if self.fork else None
         self._det_scratch = None
+        self._fill_early, self._fill_late = [], []
+        if self.fork:
+            self._split_fill(R)
         self.plan = None
         self.graph = None
         if graph:
             self._capture()
 
     # -- one step on the current stream ------------------------------------
+    # the plan's shadow: ~5 us + 2.2 ns per RoI (rpool_keys_kernel + rpool_plan_kernel on B200),
+    # during which a fill runs at ~6 TB/s
+    _SHADOW_US = staticmethod(lambda n_rois: 5.0 + 0.0022 * n_rois)
+    _FILL_BYTES_PER_US = 6.0e6
+
+    def _split_fill(self, n_rois):
+        """Which gradient maps the side stream fills: every (level, image) map, coarse levels
+        first, while the total fits the plan's shadow ('plan'), or all of them ('start')."""
+        units = []
+        for l in range(len(self.grads) - 1, -1, -1):
+            g = self.grads[l]
+            units += [g[n:n + 1] for n in range(g.shape[0])]      # one image of one level: contiguous
+        if self.fork_mode == "start":
+            self._fill_early = units
+            return
+        budget = self._SHADOW_US(n_rois) * self._FILL_BYTES_PER_US
+        used = 0
+        for u in units:
+            nbytes = u.numel() * 4
+            if not self._fill_late and used + nbytes <= budget:
+                self._fill_early.append(u)
+                used += nbytes
+            else:
+                self._fill_late.append(u)
+
+    @staticmethod
+    def _fill(units):
+        # rpool_zero_fill takes up to RPOOL_MAX_LEVELS buffers per launch
+        for i in range(0, len(units), _lib.MAX_LEVELS):
+            _engine.zero_fill(units[i:i + _lib.MAX_LEVELS])
+
     def _launch(self, marks=None):
         dev = self.rois.device
         with _engine._on(dev):
             cur = torch.cuda.current_stream(dev)
-            side = self._side
-            ev_small = ev_big = None
+            ev = None
             if marks:
                 marks[0].record(cur)
-            if self.fork:
-                side.wait_stream(cur)                            # fork
-                with torch.cuda.stream(side):
-                    _engine.zero_fill(self.grads if self.fork_mode == "start" else self.grads[1:])
-                    ev_small = side.record_event()
+            if self._fill_early:
+                self._side.wait_stream(cur)                      # fork
+                with torch.cuda.stream(self._side):
+                    self._fill(self._fill_early)
+                    ev = self._side.record_event()
             _, self.plan = _engine.forward(self.features, self.rois, self.levels, self.scales, self.sizes,
                                            sampling_ratio=self.sampling_ratio, roi_format=_lib.ROI_YX,
                                            options=self.options, workspace=self.workspace, out=self.outs)
             if marks:
                 marks[1].record(cur)
             if self.gys is not None:
-                if self.fork_mode == "split":
-                    side.wait_event(cur.record_event())          # the finest map's fill starts after the forward
-                    with torch.cuda.stream(side):
-                        _engine.zero_fill(self.grads[:1])
-                        ev_big = side.record_event()
-                    cur.wait_event(ev_small)                     # join 1: coarse maps are clean
-                    coarse = ((1 << len(self.features)) - 1) & ~1
-                    _engine.backward(self.plan, self.gys, out=self.grads, accumulate=True, levels_mask=coarse)
-                    cur.wait_event(ev_big)                       # join 2: the finest map is clean
-                    _engine.backward(self.plan, self.gys, out=self.grads, accumulate=True, levels_mask=1)
-                else:
-                    if ev_small is not None:
-                        cur.wait_event(ev_small)                 # join
-                    if self.deterministic and self._det_scratch is None:
-                        # sized once for the RoIs at hand (+25 %): later steps reuse it without a host
-                        # round trip; windows that no longer fit raise RPOOL_FLAG_DET_SCRATCH (status_flags)
-                        n = _engine.det_scratch_bytes(self.plan)
-                        self._det_scratch = torch.empty(n + n // 4 + 4096, dtype=torch.uint8, device=dev)
-                    # (no flag read-back inside the step: it would synchronise; see status_flags)
-                    _engine.backward(self.plan, self.gys, out=self.grads, accumulate=self.fork,
-                                     deterministic=self.deterministic, check_flags=False,
-                                     det_scratch=self._det_scratch)
+                if self._fill_late:
+                    self._fill(self._fill_late)
+                if ev is not None:
+                    cur.wait_event(ev)                           # join
+                if self.deterministic and self._det_scratch is None:
+                    # sized once for the RoIs at hand (+25 %): later steps reuse it without a host
+                    # round trip; windows that no longer fit raise RPOOL_FLAG_DET_SCRATCH (status_flags)
+                    n = _engine.det_scratch_bytes(self.plan)
+                    self._det_scratch = torch.empty(n + n // 4 + 4096, dtype=torch.uint8, device=dev)
+                # (no flag read-back inside the step: it would synchronise; see status_flags)
+                _engine.backward(self.plan, self.gys, out=self.grads, accumulate=self.fork,
+                                 deterministic=self.deterministic, check_flags=False,
+                                 det_scratch=self._det_scratch)
             if marks:
                 marks[2].record(cur)
 

@@ -8,7 +8,7 @@
 #include <cstdio>
 #include <cstring>
 
-#include "rpool_slide.cuh"
+#include "rpool_kernels.cuh"
 
 using namespace rpool;
 
@@ -25,36 +25,10 @@ constexpr int kMaxSmem = 227 * 1024;
 
 // rpool_options with the defaults filled in (0 = default in the ABI)
 struct Options {
-    int threads, order, force_path, split_heads, prefetch, var_fwd;
-    unsigned levels_mask;
+    int threads, order, force_path, split_heads, prefetch;
 };
 constexpr int kDefaultThreads = 128;
 constexpr int kDefaultPrefetchRows = 2;
-constexpr int kVariantRows = 1, kVariantSlide = 2;
-#ifndef RPOOL_DEFAULT_VARIANT_FWD
-#define RPOOL_DEFAULT_VARIANT_FWD 1
-#endif
-
-int fail(int code, const char *fmt, ...)
-{
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
-    va_end(ap);
-    return code;
-}
-
-int cuda_fail(cudaError_t e, const char *what)
-{
-    return fail(RPOOL_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
-}
-
-#define CUDA_TRY(expr, what)                              \
-    do {                                                  \
-        cudaError_t e__ = (expr);                         \
-        if (e__ != cudaSuccess) return cuda_fail(e__, what); \
-    } while (0)
-
 // workspace layout (r = R rounded up to 32, nb = key blocks of kKeyBlock RoIs):
 //   int32  levels[r] order[r] keys[r] rflags[r] gstart[288] bh[nb * 256] rects[4r]
 //   uint64 woff[r] sizes[r] det_total, then int32 det_err (+ padding to 16 bytes)
@@ -126,10 +100,8 @@ int read_options(const rpool_problem *p, Options &o)
         return fail(RPOOL_ERR_INVALID, "opt.prefetch_rows=%d outside [-1,16]", q.prefetch_rows);
     if (q.prefetch_rois < 0 || q.prefetch_rois > 65536)
         return fail(RPOOL_ERR_INVALID, "opt.prefetch_rois=%d outside [0,65536]", q.prefetch_rois);
-    if (q.variant_forward < 0 || q.variant_forward > 2)
-        return fail(RPOOL_ERR_INVALID, "opt.variant_forward=%d outside [0,2]", q.variant_forward);
-    if (q.levels_mask < 0 || q.levels_mask >= (1 << RPOOL_MAX_LEVELS))
-        return fail(RPOOL_ERR_INVALID, "opt.levels_mask=%d outside [0,%d)", q.levels_mask, 1 << RPOOL_MAX_LEVELS);
+    if (q.reserved[0] || q.reserved[1])
+        return fail(RPOOL_ERR_INVALID, "opt.reserved must be zero");
     o.threads = q.cta_threads ? q.cta_threads : kDefaultThreads;
     o.order = q.schedule;
     o.force_path = q.force_path;
@@ -138,8 +110,7 @@ int read_options(const rpool_problem *p, Options &o)
     if (q.prefetch_rois > 0) o.prefetch = q.prefetch_rois - 1;
     else if (q.prefetch_rows < 0) o.prefetch = -1;
     else o.prefetch = -1 - (q.prefetch_rows ? q.prefetch_rows : kDefaultPrefetchRows);
-    o.var_fwd = q.variant_forward ? q.variant_forward : RPOOL_DEFAULT_VARIANT_FWD;
-    o.levels_mask = q.levels_mask ? (unsigned)q.levels_mask : 0xffffffffu;
+
     return RPOOL_OK;
 }
 
@@ -233,7 +204,6 @@ int fill_params(const rpool_problem *p, const Workspace &w, const Options &o, bo
     const int warps = threads / 32;
     k.prefetch = o.prefetch;
     k.reverse = (bwd && o.order == RPOOL_SCHED_DEFAULT) ? 1 : 0;
-    k.levels_mask = o.levels_mask;
     k.det = 0;
     k.det_rects = w.rects;
     k.det_woff = w.woff;
@@ -250,7 +220,7 @@ int fill_params(const rpool_problem *p, const Workspace &w, const Options &o, bo
 // and only ever needs to grow, so the largest value set so far is remembered per
 // (kernel, device) and the driver call is skipped when it already covers `smem`.
 constexpr int kSmemCacheDevices = 64;
-std::atomic<int> g_smem_set[4][kSmemCacheDevices];
+std::atomic<int> g_smem_set[2][kSmemCacheDevices];
 
 template <typename Kern>
 int set_smem(Kern kern, int which, int smem)
@@ -402,15 +372,6 @@ int rpool_forward(const rpool_problem *p, void *ws, size_t ws_size, void *stream
     if (smem > kMaxSmem)
         return fail(RPOOL_ERR_UNSUPPORTED, "forward needs %d bytes of shared memory; the limit is %d",
                     smem, kMaxSmem);
-    k.variant = o.var_fwd;
-    if (o.var_fwd == kVariantSlide) {
-        rc = set_smem(rpool_forward_slide_kernel, 2, smem);
-        if (rc) return rc;
-        rpool_forward_slide_kernel<<<p->n_rois, threads, smem, static_cast<cudaStream_t>(stream)>>>(k);
-        CUDA_TRY(cudaGetLastError(), "rpool_forward_slide_kernel launch");
-        g_launches++;
-        return RPOOL_OK;
-    }
     rc = set_smem(rpool_forward_kernel, 0, smem);
     if (rc) return rc;
     rpool_forward_kernel<<<p->n_rois, threads, smem, static_cast<cudaStream_t>(stream)>>>(k);

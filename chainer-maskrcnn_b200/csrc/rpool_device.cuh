@@ -18,7 +18,6 @@ constexpr int kNT = 4;        // footprint width kept per bin and axis on the ta
 constexpr int kPMax = 32;     // largest pooled extent served by the table path (forward)
 constexpr int kPBwd = 16;     // ... by the table path of the backward kernel
 constexpr int kSW = 8;        // window columns a chunk of bins may span (forward registers)
-constexpr int kSL = 6;        // ... in the "slide" forward kernel, which keeps three such buffers per lane
 constexpr int kExt = 64;      // largest window extent (cells per axis) of the backward table path
 #ifndef RPOOL_MIN_BLOCKS
 #define RPOOL_MIN_BLOCKS 2   // resident CTAs per SM the pooling kernels are register-capped for
@@ -66,8 +65,6 @@ struct KParams {
     int rec_stride;
     int rec_head;    // first head part of the stored record this launch uses (0 unless heads are split)
     int force_path;
-    int variant;     // forward kernel variant of this launch (1 = rows, 2 = slide)
-    unsigned levels_mask;  // backward: only RoIs whose level bit is set take part
 };
 
 // ---------------------------------------------------------------------------
@@ -206,12 +203,6 @@ struct HeadCtl {
     unsigned char pad1_[4];
     int cx0[kPMax];                      // first column of each chunk's span
     unsigned long long ccnt[kPMax];      // bins per span offset, one byte each
-    // the same cut for spans of kSL columns (slide forward kernel)
-    unsigned char cstart6[kPMax + 4];
-    int nchunk6;
-    int cx06[kPMax];
-    unsigned long long ccnt6[kPMax];
-    int pad2_[2];
 };
 
 // One RoI's record.  rpool_tables_kernel builds it once per plan (all RoIs in

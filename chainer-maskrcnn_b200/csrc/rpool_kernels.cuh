@@ -658,7 +658,6 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     RoiCtx c;
     ctx_from_record(P, ctl, c);
     if (!c.valid) return;
-    if (!((P.levels_mask >> c.lvl) & 1u)) return;     // this launch covers other levels (opt.levels_mask)
     const int need = kRecShape | kRecFits;
     bool table_ok = (ctl->flags & need) == need && P.force_path != kPathGeneric && pointers_aligned(P, c.L);
     for (int h = 0; h < P.n_heads; ++h) table_ok = table_ok && P.PH[h] <= kPBwd && P.PW[h] <= kPBwd;
@@ -861,14 +860,14 @@ __device__ __forceinline__ void warp_build_tables(const KParams &P, const RoiCtx
 // Cuts every pooled size's bins into chunks whose x footprints fit a span of kSW columns
 // (as build_chunks), one lane per bin: the end of a chunk is the first bin that no longer
 // fits, found with one ballot; its per-offset bin counts and column mask are reductions.
-template <int kSpan>
 __device__ __forceinline__ void warp_build_chunks(const KParams &P, const RoiCtx &c, BlockCtl *ctl, int max_bins,
                                                   int lane)
 {
     for (int h = 0; h < P.n_heads; ++h) {
-        unsigned char *cstart = kSpan == kSW ? ctl->hd[h].cstart : ctl->hd[h].cstart6;
-        int *cx0 = kSpan == kSW ? ctl->hd[h].cx0 : ctl->hd[h].cx06;
-        unsigned long long *ccnt = kSpan == kSW ? ctl->hd[h].ccnt : ctl->hd[h].ccnt6;
+        constexpr int kSpan = kSW;
+        unsigned char *cstart = ctl->hd[h].cstart;
+        int *cx0 = ctl->hd[h].cx0;
+        unsigned long long *ccnt = ctl->hd[h].ccnt;
         const AxisTab &xt = ctl->hd[h].tab[1];
         const int PW = P.PW[h];
         const int W = c.L.W;
@@ -902,14 +901,14 @@ __device__ __forceinline__ void warp_build_chunks(const KParams &P, const RoiCtx
                 cstart[n] = (unsigned char)pa;
                 cx0[n] = x0;
                 ccnt[n] = ((unsigned long long)c_hi << 32) | c_lo;
-                if (kSpan == kSW) ctl->hd[h].cmask[n] = (unsigned char)(msk & 0xffu);
+                ctl->hd[h].cmask[n] = (unsigned char)(msk & 0xffu);
             }
             ++n;
             pa = pe;
         }
         if (lane == 0) {
             cstart[n] = (unsigned char)PW;
-            if (kSpan == kSW) ctl->hd[h].nchunk = n; else ctl->hd[h].nchunk6 = n;
+            ctl->hd[h].nchunk = n;
         }
     }
     __syncwarp();
@@ -1004,12 +1003,7 @@ rpool_plan_kernel(const __grid_constant__ KParams P, const __grid_constant__ Pla
         __syncwarp();
         if (c.valid && c.fast_ok) {      // (uniform) otherwise the consumer takes the generic path
             warp_build_tables(P, c, bwd != 0, ctl, lane);
-            if (ctl->flags & kRecFits) {
-                warp_build_chunks<kSW>(P, c, ctl, kPMax, lane);
-                // (a footprint of kNT cells always fits a span of kSL >= kNT columns; a map narrower
-                // than kSW columns never reaches the table paths)
-                if (!bwd) warp_build_chunks<kSL>(P, c, ctl, kPMax, lane);
-            }
+            if (ctl->flags & kRecFits) warp_build_chunks(P, c, ctl, kPMax, lane);
         }
         __syncwarp();
         const uint4 *src = reinterpret_cast<const uint4 *>(ctl);

@@ -105,13 +105,7 @@ typedef struct rpool_options {
                              * 0 = default (2), -1 = off, 1..16 */
     int32_t prefetch_rois;  /* backward, rows variant: > 0 replaces the row-ahead prefetch by the whole
                              * RoI of the CTA scheduled prefetch_rois - 1 slots later */
-    int32_t variant_forward;  /* 0 = default kernel; 1 = "rows" (one bin row per warp task);
-                               * 2 = "slide" (one chunk per warp task, window rows loaded once and
-                               * kept in registers while the footprints slide over them) */
-    int32_t levels_mask;      /* rpool_backward: bit l set = RoIs of level l take part; 0 = all.  Lets a
-                               * caller split the backward pass by level, e.g. coarse levels first while
-                               * the (large) finest gradient map is still being zero-filled on another
-                               * stream (accumulate = 1; the step helper of the Python package does this) */
+    int32_t reserved[2];    /* must be zero */
 } rpool_options;
 
 /* One pyramid level.  `data` is the feature map in rpool_forward (read) and

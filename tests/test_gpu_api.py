@@ -238,7 +238,7 @@ def test_step_is_cuda_graph_capturable_and_replays_on_new_rois():
             assert oracle.rel_err(grads[l].cpu().numpy(), want_g[l]) <= 1e-4
 
 
-@pytest.mark.parametrize("fork", ["split", "start", "none"])
+@pytest.mark.parametrize("fork", ["plan", "start", "none"])
 @pytest.mark.parametrize("graph", [True, False])
 @pytest.mark.parametrize("sizes,S", [([7], 2), ([7, 14], 1)])
 def test_fused_step_helper_forks_the_zero_fill_and_replays(graph, sizes, S, fork):
@@ -266,10 +266,10 @@ def test_fused_step_helper_forks_the_zero_fill_and_replays(graph, sizes, S, fork
         outs, grads = step.run()
         torch.cuda.synchronize()
         if not graph:
-            # keys + plan + forward, then zero fill and one backward launch per pooled size --
-            # both twice when the fill is split (coarse levels / finest level)
-            parts = 2 if fork == "split" else 1
-            assert _lib.launch_count() - n0 == 3 + parts * (1 + len(sizes))
+            # keys + plan + forward + one backward launch per pooled size, and the zero fill: one
+            # launch per <= 8 (level, image) maps when it is forked (early and late part), one otherwise
+            fills = 1 if fork == "none" else -(-len(step._fill_early) // 8) + -(-len(step._fill_late) // 8)
+            assert _lib.launch_count() - n0 == 3 + len(sizes) + fills
         lv = oracle.levels_for_pyramid(r[:, 1:], L)
         want_g = [np.zeros_like(f) for f in feats]
         for o, P, gy in zip(outs, sizes, gys):

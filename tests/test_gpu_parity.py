@@ -179,11 +179,10 @@ def test_levels_random_million_bit_exact():
 @pytest.mark.parametrize("path,prefetch", [("auto", {}), ("generic", dict(prefetch_rows=-1)),
                                            ("table", dict(prefetch_rois=1)), ("table", dict(prefetch_rois=8)),
                                            ("table", dict(prefetch_rows=1)), ("table", dict(prefetch_rows=-1))])
-@pytest.mark.parametrize("variant", [_lib.VARIANT_ROWS, _lib.VARIANT_SLIDE])
 @pytest.mark.parametrize("mode_name,S", [("chainer", 1), ("caffe2", 1), ("caffe2", 2), ("caffe2", 3)])
-def test_fused_vs_oracle(path, prefetch, variant, mode_name, S):
+def test_fused_vs_oracle(path, prefetch, mode_name, S):
     rng, feats, rois, levels, scales = make_case(seed=S * 7 + len(path))
-    opt = dict(force_path=PATHS[path], variant_forward=variant, **prefetch)
+    opt = dict(force_path=PATHS[path], **prefetch)
     mode = _lib.COORD_CHAINER if mode_name == "chainer" else _lib.COORD_CAFFE2
     sizes = [7, 14]
     gys = [synth.make_gy(rng, rois.shape[0], feats[0].shape[1], P) for P in sizes]
@@ -197,13 +196,12 @@ def test_fused_vs_oracle(path, prefetch, variant, mode_name, S):
         assert oracle.rel_err(g, w) <= BWD_TOL
 
 
-@pytest.mark.parametrize("variant", [_lib.VARIANT_ROWS, _lib.VARIANT_SLIDE])
 @pytest.mark.parametrize("threads", [32, 64, 224, 256])
-def test_block_sizes(threads, variant):
+def test_block_sizes(threads):
     rng, feats, rois, levels, scales = make_case(seed=3, C=128, per_img=60)
     gys = [synth.make_gy(rng, rois.shape[0], 128, 14)]
     outs, grads, _ = run_fused(feats, rois, levels, scales, [14], 2, gys=gys,
-                               options=dict(cta_threads=threads, variant_forward=variant))
+                               options=dict(cta_threads=threads))
     want, wgrads = oracle_fused(feats, rois, levels, scales, [14], 2, "caffe2", gys)
     assert oracle.rel_err(outs[0], want[0]) <= FWD_TOL
     for g, w in zip(grads, wgrads):
@@ -482,26 +480,6 @@ def test_deterministic_backward_edge_cases():
     with pytest.raises(_lib.RpoolError):
         _engine.backward(plan, [dev(gy)], deterministic=True, det_scratch=small)
     assert _engine.status_flags(plan) & _lib.FLAG_DET_SCRATCH
-
-
-def test_backward_split_by_level_mask():
-    """opt.levels_mask: the backward pass over the coarse levels' RoIs and over the finest
-    level's RoIs as two launches (what FusedStep does around the forked zero fill) adds up to
-    the single launch."""
-    rng, feats, rois, levels, scales = make_case(seed=51, C=32, per_img=120)
-    gy = synth.make_gy(rng, rois.shape[0], 32, 14)
-    f = [dev(x, True) for x in feats]
-    _, plan = _engine.forward(f, dev(rois), None, scales, [14], sampling_ratio=2)
-    whole = [host(g) for g in _engine.backward(plan, [dev(gy, True)])]
-    parts = [torch.zeros_like(x) for x in f]
-    _engine.backward(plan, [dev(gy, True)], out=parts, accumulate=True, levels_mask=0b1110)
-    only_coarse = [host(g) for g in parts]
-    assert float(np.abs(only_coarse[0]).max()) == 0.0 and float(np.abs(only_coarse[3]).max()) > 0.0
-    _engine.backward(plan, [dev(gy, True)], out=parts, accumulate=True, levels_mask=0b0001)
-    for a, w in zip(parts, whole):
-        assert oracle.rel_err(host(a), w) <= BWD_TOL
-    with pytest.raises(ValueError):
-        _engine.backward(plan, [dev(gy, True)], levels_mask=1)
 
 
 @pytest.mark.parametrize("deterministic", [False, True])
