@@ -29,6 +29,27 @@ struct Options {
 };
 constexpr int kDefaultThreads = 128;
 constexpr int kDefaultPrefetchRows = 2;
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(RPOOL_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CUDA_TRY(expr, what)                              \
+    do {                                                  \
+        cudaError_t e__ = (expr);                         \
+        if (e__ != cudaSuccess) return cuda_fail(e__, what); \
+    } while (0)
+
 // workspace layout (r = R rounded up to 32, nb = key blocks of kKeyBlock RoIs):
 //   int32  levels[r] order[r] keys[r] rflags[r] gstart[288] bh[nb * 256] rects[4r]
 //   uint64 woff[r] sizes[r] det_total, then int32 det_err (+ padding to 16 bytes)
