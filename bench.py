@@ -53,11 +53,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every step from Python instead of replaying the captured graph")
-    ap.add_argument("--fork", default="plan", choices=["plan", "start", "none"],
-                    help="where the gradient zero fill runs: 'plan' = what fits beside rpool_plan on a side "
-                         "stream, the rest right before the backward launch; 'start' = all of it beside "
-                         "plan + forward; 'none' = inside rpool_backward")
-    ap.add_argument("--no-fork", action="store_true", help="same as --fork none")
+    ap.add_argument("--fork", action="store_true",
+                    help="fork the gradient zero fill to a side stream beside plan + forward (FusedStep "
+                         "fork_zero_fill=True); default: inside rpool_backward")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-strong", action="store_true",
                     help="N > 1: skip the sharded configs[3] run attached as 'strong'")
@@ -482,7 +480,7 @@ def run_reference(args):
 # GPU arm
 # ---------------------------------------------------------------------------
 def fork_mode(args):
-    return "none" if args.no_fork else args.fork
+    return bool(args.fork)
 
 
 def _parse_opts(text):
@@ -689,7 +687,6 @@ def run_b200(args):
     step = pkg.FusedStep(feats, rois, None, scales, sizes, S, gys=gys,
                          graph=not args.no_graph, deterministic=args.deterministic,
                          fork_zero_fill=fork_mode(args), options=opts)
-    late = sum(u.numel() * 4 for u in step._fill_late)     # bytes of the fill left inside the backward window
     n0 = _lib.launch_count()
     step.run(marks=[torch.cuda.Event() for _ in range(3)])       # launched from Python: counted
     launches_per_step = _lib.launch_count() - n0
@@ -703,12 +700,15 @@ def run_b200(args):
     # ---- where the time goes: the same step launched from Python with events around the
     # forward and backward launches, and the r01 sequence (no fork, no graph) beside it ----
     fwd_ms, bwd_ms, launched_ms = _marked(step, K, device)
-    serial = pkg.FusedStep(feats, rois, None, scales, sizes, S, gys=gys, graph=False,
-                           deterministic=args.deterministic, fork_zero_fill=False, options=opts)
-    for _ in range(W):
-        serial.run()
-    s_fwd, s_bwd, s_tot = _marked(serial, K, device)
-    del serial
+    if forked:
+        serial = pkg.FusedStep(feats, rois, None, scales, sizes, S, gys=gys, graph=False,
+                               deterministic=args.deterministic, fork_zero_fill=False, options=opts)
+        for _ in range(W):
+            serial.run()
+        s_fwd, s_bwd, s_tot = _marked(serial, K, device)
+        del serial
+    else:
+        s_fwd, s_bwd, s_tot = fwd_ms, bwd_ms, launched_ms
 
     # ---- end to end through the public host-array API ---------------------
     e2e = None
@@ -793,10 +793,9 @@ def run_b200(args):
 
     levels_np = _engine.read_plan(_engine.make_plan(shapes, rois, None, scales, sizes, S))[0]
     ab = algorithmic_bytes(cfg, shapes, rois_np, levels_np, scales, S)
-    forked = fork_mode(args) != "none" and not args.deterministic
+    forked = fork_mode(args) and not args.deterministic
     # dominant launch: forward, or backward (with the fill forked away it is the scatter alone)
-    # the backward window (forward launch done -> backward launch done) holds the late part of the fill
-    bwd_bytes = ab["bwd"] if not forked else ab["bwd_scatter"] + late
+    bwd_bytes = ab["bwd"] if not forked else ab["bwd_scatter"]
     dom = "backward" if bwd_ms >= fwd_ms else "forward"
     dom_ms = bwd_ms if dom == "backward" else fwd_ms
     dom_bytes = bwd_bytes if dom == "backward" else ab["fwd"]
@@ -812,13 +811,12 @@ def run_b200(args):
                           "ncu --set full, per launch)",
         "peak_source": peak_src,
         "ncu": ncu_view(args.config, S),
-        "kernel": ("rpool_backward_kernel" + ("" if (forked and not late) else " + rpool_zero_kernel")
+        "kernel": ("rpool_backward_kernel" + ("" if forked else " + rpool_zero_kernel")
                    if dom == "backward"
                    else "rpool_plan_kernel + rpool_forward_kernel"),
         "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms,
-        "bytes_definition": "fwd = O + U*C*4 + 20R; bwd = O + F + 20R (SURVEY 8d).  With part of the fill on the "
-                            "forked stream the backward window is O + 2*U*C*4 + 20R (gy read once, touched cells "
-                            "read and written) + the bytes of the fill that still runs inside it",
+        "bytes_definition": "fwd = O + U*C*4 + 20R; bwd = O + F + 20R (SURVEY 8d); with --fork the fill runs beside "
+                            "plan + forward and the backward launch alone is O + 2*U*C*4 + 20R",
         "forward": {"ms": fwd_ms, "bytes": int(ab["fwd"]), "GBps": ab["fwd"] / (fwd_ms * 1e-3) / 1e9,
                     "frac": frac(ab["fwd"], fwd_ms),
                     "note": "plan + forward launches" + (", the forked zero fill runs beside them" if forked else "")},
@@ -869,7 +867,7 @@ def run_b200(args):
         "data": "synthetic",
         "config": bench_config(cfg, args.config, full_R, S, args.shard, world),
         "how": {"api": "chainer_maskrcnn_b200.FusedStep.run()",
-                "cuda_graph": graphed, "zero_fill_forked": fork_mode(args) if forked else "none", "deterministic": bool(args.deterministic),
+                "cuda_graph": graphed, "zero_fill_forked": bool(forked), "deterministic": bool(args.deterministic),
                 "options": opts, "build_id": _lib.build_id(),
                 "layout": "channels-last features / pooled maps / gradients resident in HBM",
                 "sharding": "by image, one process per GPU, no data-path collective"},

@@ -4,16 +4,14 @@ What a training loop does around the heads, packaged so that the launch overhead
 and the gradient zero fill leave the critical path:
 
   * every buffer (plan workspace, pooled maps, dense gradients) is allocated once;
-  * the zero fill of the dense gradients depends on nothing, so part of it is forked to
-    a side stream and rpool_backward runs with ``accumulate = 1`` (rpool_zero_fill in
-    include/rpool_b200.h exists for exactly this).  Which part: rpool_plan moves almost
-    no bytes, so a fill beside it is free, whereas the forward pass is bound by HBM
-    writes and a fill beside it only takes its bandwidth (measured: a fill forked
-    beside plan + forward makes the forward launch 30 us slower and the step no
-    faster).  ``fork_zero_fill="plan"`` (default) therefore fills, on the side stream,
-    as many (level, image) maps as fit in the plan's shadow, coarse levels first, and
-    the rest on the main stream right before the backward launch; ``"start"`` forks
-    the whole fill, ``"none"`` leaves it inside rpool_backward;
+  * the zero fill of the dense gradients depends on nothing, so it CAN be forked to a
+    side stream (``fork_zero_fill=True``: rpool_zero_fill beside plan + forward, then
+    rpool_backward with ``accumulate = 1``).  Inside this helper that does not pay and
+    is off by default: the forward pass is bound by HBM writes, a fill beside it only
+    takes its bandwidth (measured on configs[0..3]: forward launch +25 us, step
+    0 .. +3 % slower than the plain sequence once the step is a CUDA graph).  A
+    training loop has better places to hide the fill (the heads' own compute between
+    the two pooling calls); rpool_zero_fill exists for that;
   * with ``graph=True`` the whole step (fork and join included) is captured once
     into a CUDA graph and replayed: the RoIs, features and upstream gradients are
     read from their device buffers at replay time, so new data is written into the
@@ -39,7 +37,7 @@ class FusedStep(object):
     gradient per pooled size (None: forward only)."""
 
     def __init__(self, features, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
-                 gys=None, graph=True, deterministic=False, fork_zero_fill="plan", options=None):
+                 gys=None, graph=True, deterministic=False, fork_zero_fill=False, options=None):
         self.features = list(features)
         self.rois, self.levels = rois, levels
         self.scales = list(spatial_scales)
@@ -64,55 +62,15 @@ class FusedStep(object):
         n = _lib.lib().rpool_workspace_bytes_ex(R, len(self.sizes), coord)
         self.workspace = torch.empty(n, dtype=torch.uint8, device=dev)
         # the deterministic variant writes every gradient cell itself: nothing to fork
-        mode = {True: "plan", False: "none", None: "none"}.get(fork_zero_fill, fork_zero_fill)
-        if mode not in ("plan", "start", "none"):
-            raise ValueError("fork_zero_fill must be 'plan', 'start', 'none' or a bool")
-        if self.gys is None or self.deterministic:
-            mode = "none"
-        self.fork_mode = mode
-        self.fork = mode != "none"
+        self.fork = bool(fork_zero_fill) and self.gys is not None and not self.deterministic
         self._side = torch.cuda.Stream(device=dev) if self.fork else None
         self._det_scratch = None
-        self._fill_early, self._fill_late = [], []
-        if self.fork:
-            self._split_fill(R)
         self.plan = None
         self.graph = None
         if graph:
             self._capture()
 
     # -- one step on the current stream ------------------------------------
-    # the plan's shadow: ~5 us + 2.2 ns per RoI (rpool_keys_kernel + rpool_plan_kernel on B200),
-    # during which a fill runs at ~6 TB/s
-    _SHADOW_US = staticmethod(lambda n_rois: 5.0 + 0.0022 * n_rois)
-    _FILL_BYTES_PER_US = 6.0e6
-
-    def _split_fill(self, n_rois):
-        """Which gradient maps the side stream fills: every (level, image) map, coarse levels
-        first, while the total fits the plan's shadow ('plan'), or all of them ('start')."""
-        units = []
-        for l in range(len(self.grads) - 1, -1, -1):
-            g = self.grads[l]
-            units += [g[n:n + 1] for n in range(g.shape[0])]      # one image of one level: contiguous
-        if self.fork_mode == "start":
-            self._fill_early = units
-            return
-        budget = self._SHADOW_US(n_rois) * self._FILL_BYTES_PER_US
-        used = 0
-        for u in units:
-            nbytes = u.numel() * 4
-            if not self._fill_late and used + nbytes <= budget:
-                self._fill_early.append(u)
-                used += nbytes
-            else:
-                self._fill_late.append(u)
-
-    @staticmethod
-    def _fill(units):
-        # rpool_zero_fill takes up to RPOOL_MAX_LEVELS buffers per launch
-        for i in range(0, len(units), _lib.MAX_LEVELS):
-            _engine.zero_fill(units[i:i + _lib.MAX_LEVELS])
-
     def _launch(self, marks=None):
         dev = self.rois.device
         with _engine._on(dev):
@@ -120,10 +78,10 @@ class FusedStep(object):
             ev = None
             if marks:
                 marks[0].record(cur)
-            if self._fill_early:
+            if self.fork:
                 self._side.wait_stream(cur)                      # fork
                 with torch.cuda.stream(self._side):
-                    self._fill(self._fill_early)
+                    _engine.zero_fill(self.grads)
                     ev = self._side.record_event()
             _, self.plan = _engine.forward(self.features, self.rois, self.levels, self.scales, self.sizes,
                                            sampling_ratio=self.sampling_ratio, roi_format=_lib.ROI_YX,
@@ -131,8 +89,6 @@ class FusedStep(object):
             if marks:
                 marks[1].record(cur)
             if self.gys is not None:
-                if self._fill_late:
-                    self._fill(self._fill_late)
                 if ev is not None:
                     cur.wait_event(ev)                           # join
                 if self.deterministic and self._det_scratch is None:

@@ -238,7 +238,7 @@ def test_step_is_cuda_graph_capturable_and_replays_on_new_rois():
             assert oracle.rel_err(grads[l].cpu().numpy(), want_g[l]) <= 1e-4
 
 
-@pytest.mark.parametrize("fork", ["plan", "start", "none"])
+@pytest.mark.parametrize("fork", [False, True])
 @pytest.mark.parametrize("graph", [True, False])
 @pytest.mark.parametrize("sizes,S", [([7], 2), ([7, 14], 1)])
 def test_fused_step_helper_forks_the_zero_fill_and_replays(graph, sizes, S, fork):
@@ -256,7 +256,7 @@ def test_fused_step_helper_forks_the_zero_fill_and_replays(graph, sizes, S, fork
     rois = torch.from_numpy(rois_a).cuda()
     step = pkg.FusedStep([cl(f) for f in feats], rois, None, scales, sizes, S, gys=[cl(g) for g in gys],
                          graph=graph, fork_zero_fill=fork)
-    assert (step.graph is not None) == graph and step.fork_mode == fork
+    assert (step.graph is not None) == graph and step.fork == fork
     mode = "chainer" if S == 1 else "caffe2"
     for r in (rois_a, rois_b, rois_a):
         rois.copy_(torch.from_numpy(r).cuda())
@@ -266,10 +266,8 @@ def test_fused_step_helper_forks_the_zero_fill_and_replays(graph, sizes, S, fork
         outs, grads = step.run()
         torch.cuda.synchronize()
         if not graph:
-            # keys + plan + forward + one backward launch per pooled size, and the zero fill: one
-            # launch per <= 8 (level, image) maps when it is forked (early and late part), one otherwise
-            fills = 1 if fork == "none" else -(-len(step._fill_early) // 8) + -(-len(step._fill_late) // 8)
-            assert _lib.launch_count() - n0 == 3 + len(sizes) + fills
+            # keys + plan + forward + zero fill + one backward launch per pooled size
+            assert _lib.launch_count() - n0 == 4 + len(sizes)
         lv = oracle.levels_for_pyramid(r[:, 1:], L)
         want_g = [np.zeros_like(f) for f in feats]
         for o, P, gy in zip(outs, sizes, gys):
