@@ -682,6 +682,7 @@ def run_b200(args):
     feats, rois, gys = _device_tensors(cfg, shapes, rois_np, device, seed=17 + 100 * rank)
     W = max(args.warmup, 3)
     K = args.steps
+    forked = fork_mode(args) and not args.deterministic
 
     # ---- the step: the package's helper (static buffers, forked zero fill, CUDA graph) ----
     step = pkg.FusedStep(feats, rois, None, scales, sizes, S, gys=gys,
@@ -793,7 +794,6 @@ def run_b200(args):
 
     levels_np = _engine.read_plan(_engine.make_plan(shapes, rois, None, scales, sizes, S))[0]
     ab = algorithmic_bytes(cfg, shapes, rois_np, levels_np, scales, S)
-    forked = fork_mode(args) and not args.deterministic
     # dominant launch: forward, or backward (with the fill forked away it is the scatter alone)
     bwd_bytes = ab["bwd"] if not forked else ab["bwd_scatter"]
     dom = "backward" if bwd_ms >= fwd_ms else "forward"

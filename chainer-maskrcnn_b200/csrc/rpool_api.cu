@@ -27,7 +27,13 @@ constexpr int kMaxSmem = 227 * 1024;
 struct Options {
     int threads, order, force_path, split_heads, prefetch;
 };
+// CTA size of the pooling kernels when opt.cta_threads is 0: 4 warps per RoI, 4 such CTAs resident
+// per SM (register-limited).  A problem that does not even fill one wave of those (148 SMs x 4) is
+// bound by the latency of its longest CTA, not by throughput: 8 warps per RoI halve that chain
+// (configs[0], 512 RoIs: 62 -> 55 us per step; configs[1] and [3] lose 7-9 % with 8 warps).
 constexpr int kDefaultThreads = 128;
+constexpr int kSmallProblemThreads = 256;
+constexpr int kOneWaveRois = 148 * 4;
 constexpr int kDefaultPrefetchRows = 2;
 
 int fail(int code, const char *fmt, ...)
@@ -123,7 +129,8 @@ int read_options(const rpool_problem *p, Options &o)
         return fail(RPOOL_ERR_INVALID, "opt.prefetch_rois=%d outside [0,65536]", q.prefetch_rois);
     if (q.reserved[0] || q.reserved[1])
         return fail(RPOOL_ERR_INVALID, "opt.reserved must be zero");
-    o.threads = q.cta_threads ? q.cta_threads : kDefaultThreads;
+    o.threads = q.cta_threads ? q.cta_threads
+                              : (p->n_rois <= kOneWaveRois ? kSmallProblemThreads : kDefaultThreads);
     o.order = q.schedule;
     o.force_path = q.force_path;
     o.split_heads = q.fuse_heads_backward ? 0 : 1;

@@ -723,8 +723,9 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
 // asks for -- and writes the RoI's record (footprint tables + chunking, for the
 // forward geometry and, in RPOOL_COORD_CHAINER mode, a second one for the backward
 // geometry) at that slot.  There is no single-CTA sort on the critical path:
-//   R <= kPlanSingle one launch: every warp derives the keys of all RoIs itself
-//                    (R / 32 RoIs per lane, 20 bytes each, L1/L2 hits);
+//   R <= kPlanSingle one launch: every CTA derives the keys of all RoIs once into shared
+//                    memory (R / 128 RoIs per thread, 20 bytes each, L1/L2 hits) and its
+//                    warps rank their RoIs from there;
 //   R  > kPlanSingle rpool_keys_kernel first writes the keys and one histogram per
 //                    block of kKeyBlock RoIs; a plan CTA then sums the histogram
 //                    entries that precede (key_i, block_i) and ranks its RoI inside
@@ -769,7 +770,7 @@ constexpr int kPlanWarps = 4;               // RoIs per plan CTA: one warp each
 constexpr int kPlanThreads = kPlanWarps * 32;
 constexpr int kPlanMaxKeys = 256;
 constexpr int kKeyBlock = 1024;             // RoIs per block of rpool_keys_kernel
-constexpr int kPlanSingle = 64;             // up to this many RoIs every plan warp derives all keys itself
+constexpr int kPlanSingle = 1024;            // up to this many RoIs every plan warp derives all keys itself
 
 // Level (clipped to the pyramid, maskrcnn.py:141), schedule key and flags of RoI i.
 __device__ __forceinline__ int plan_key(const PlanParams &p, int i, int &lvl_out, int &flags_out)
@@ -920,9 +921,19 @@ rpool_plan_kernel(const __grid_constant__ KParams P, const __grid_constant__ Pla
 {
     __shared__ __align__(16) BlockCtl ctl_s[kPlanWarps];
     __shared__ int s_hist[kPlanMaxKeys + 1];
+    __shared__ unsigned char s_keys[kPlanSingle];  // single-launch mode: every RoI's key (K <= 256)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i = blockIdx.x * kPlanWarps + warp;
     const bool first = (blockIdx.x == 0);         // this CTA also writes gstart
+
+    // ---- single-launch mode: the CTA derives all keys once, its warps rank from shared memory
+    if (p.n_blocks == 0 && p.order_mode != RPOOL_SCHED_INPUT) {
+        for (int j = tid; j < p.R; j += kPlanThreads) {
+            int l2, f2;
+            s_keys[j] = (unsigned char)plan_key(p, j, l2, f2);
+        }
+        __syncthreads();
+    }
 
     // ---- gstart: first slot of every key (CTA 0, all its warps)
     if (first && p.gstart) {
@@ -930,10 +941,7 @@ rpool_plan_kernel(const __grid_constant__ KParams P, const __grid_constant__ Pla
         __syncthreads();
         if (p.order_mode != RPOOL_SCHED_INPUT) {
             if (p.n_blocks == 0) {
-                for (int j = tid; j < p.R; j += kPlanThreads) {
-                    int l2, f2;
-                    atomicAdd(&s_hist[plan_key(p, j, l2, f2)], 1);
-                }
+                for (int j = tid; j < p.R; j += kPlanThreads) atomicAdd(&s_hist[s_keys[j]], 1);
             } else {
                 const int n = p.n_blocks * p.K;
                 for (int e = tid; e < n; e += kPlanThreads) atomicAdd(&s_hist[e % p.K], __ldg(p.bh + e));
@@ -961,8 +969,7 @@ rpool_plan_kernel(const __grid_constant__ KParams P, const __grid_constant__ Pla
         int acc = 0;
         if (p.n_blocks == 0) {
             for (int j = lane; j < p.R; j += 32) {
-                int l2, f2;
-                const int kj = plan_key(p, j, l2, f2);
+                const int kj = s_keys[j];
                 acc += (kj < key || (kj == key && j < i)) ? 1 : 0;
             }
         } else {

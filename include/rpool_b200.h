@@ -96,7 +96,8 @@ typedef enum rpool_path {
 } rpool_path;
 
 typedef struct rpool_options {
-    int32_t cta_threads;    /* CTA size of the pooling kernels: 0 = 128; multiple of 32 in [32,256] */
+    int32_t cta_threads;    /* CTA size of the pooling kernels: multiple of 32 in [32,256]; 0 = 128, or 256
+                             * for a problem of at most 592 RoIs (less than one wave of 128-thread CTAs) */
     int32_t schedule;       /* rpool_schedule */
     int32_t force_path;     /* rpool_path */
     int32_t fuse_heads_backward; /* 0: one backward launch per pooled size; 1: one launch for both */

@@ -55,6 +55,9 @@ CONFIGS = {
             rois_per_image=512, out_sizes=[14], n_levels=4, channels=256, aspect=(1.5, 3.0)),
     3: dict(name="cfg3_box7_mask14_16img_800x1333_1000rois", n_images=16, height=800, width=1333,
             rois_per_image=1000, out_sizes=[7, 14], n_levels=4, channels=256, aspect=(0.5, 2.0)),
+    # what ONE of 8 GPUs holds when configs[3] is sharded by image (tuning aid: same shapes, 2 images)
+    13: dict(name="cfg3_one_eighth_2img_1000rois", n_images=2, height=800, width=1333,
+             rois_per_image=1000, out_sizes=[7, 14], n_levels=4, channels=256, aspect=(0.5, 2.0)),
 }
 
 
