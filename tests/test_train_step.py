@@ -113,6 +113,9 @@ def test_train_step_b200_pooling_matches_torchvision():
                         m.extractor.conv1.weight.grad.clone(), chain.last["n_sample"])
     assert out["b200"][3] == out["torchvision"][3]
     assert out["b200"][0] == pytest.approx(out["torchvision"][0], rel=1e-5)
-    for i in (1, 2):
+    # the lateral conv right under the pooled level sees the pooling gradient almost directly; conv1's
+    # weight gradient went through the whole backbone backwards (atomics in both pooling back ends, cuDNN
+    # reductions): it agrees to ~8e-4 of its largest entry and moves by 1e-4 from run to run
+    for i, tol in ((1, 1e-4), (2, 5e-3)):
         a, r = out["b200"][i], out["torchvision"][i]
-        assert float((a - r).abs().max() / r.abs().max()) <= 1e-3
+        assert float((a - r).abs().max() / r.abs().max()) <= tol
