@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--fork", action="store_true",
                     help="fork the gradient zero fill to a side stream beside plan + forward (FusedStep "
                          "fork_zero_fill=True); default: inside rpool_backward")
+    ap.add_argument("--no-tail", action="store_true",
+                    help="plain stream order for the zero fill (FusedStep fill_in_tail=False)")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-strong", action="store_true",
                     help="N > 1: skip the sharded configs[3] run attached as 'strong'")
@@ -591,7 +593,7 @@ def strong_scaling(args, world, rank, device, dist, peak, opts):
     feats, rois, gys = _device_tensors(cfg, shapes, rois_np, device, seed=1234)     # same on every rank
     K = max(5, min(args.steps, 30))
     full = pkg.FusedStep(feats, rois, None, scales, cfg["out_sizes"], S, gys=gys, graph=not args.no_graph,
-                         fork_zero_fill=fork_mode(args), options=opts)
+                         fork_zero_fill=fork_mode(args), options=opts, fill_in_tail=not args.no_tail)
     for _ in range(3):
         full.run()
     t1, _ = _timed(full.run, K, world, device, dist)
@@ -604,7 +606,7 @@ def strong_scaling(args, world, rank, device, dist, peak, opts):
     f_loc = [f[idx].contiguous(memory_format=torch.channels_last) for f in feats]
     g_loc = [g[ridx].contiguous(memory_format=torch.channels_last) for g in gys]
     part = pkg.FusedStep(f_loc, torch.from_numpy(local).to(device), None, scales, cfg["out_sizes"], S,
-                         gys=g_loc, graph=not args.no_graph, fork_zero_fill=fork_mode(args), options=opts)
+                         gys=g_loc, graph=not args.no_graph, fork_zero_fill=fork_mode(args), options=opts, fill_in_tail=not args.no_tail)
     for _ in range(3):
         part.run()
     tn, _ = _timed(part.run, K, world, device, dist)
@@ -687,7 +689,7 @@ def run_b200(args):
     # ---- the step: the package's helper (static buffers, forked zero fill, CUDA graph) ----
     step = pkg.FusedStep(feats, rois, None, scales, sizes, S, gys=gys,
                          graph=not args.no_graph, deterministic=args.deterministic,
-                         fork_zero_fill=fork_mode(args), options=opts)
+                         fork_zero_fill=fork_mode(args), options=opts, fill_in_tail=not args.no_tail)
     n0 = _lib.launch_count()
     step.run(marks=[torch.cuda.Event() for _ in range(3)])       # launched from Python: counted
     launches_per_step = _lib.launch_count() - n0

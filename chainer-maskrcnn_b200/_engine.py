@@ -315,11 +315,14 @@ def forward(features, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
 
 
 def backward(plan, gys, deterministic=False, out=None, accumulate=False, check_flags=True,
-             det_scratch=None):
+             det_scratch=None, fill_in_tail=False):
     """Dense feature gradients (channels-last memory, logical (N,C,H,W)) for
     every level from the pooled gradients ``gys`` (one per head).  ``out``: optional
     preallocated gradient tensors to write into; with ``accumulate=True`` the result
     is added to what ``out`` already holds (no zero fill: rpool_problem.accumulate).
+    ``fill_in_tail``: the zero fill may start while the kernel queued before this call on the
+    stream is still draining; only when that kernel does not touch the gradient buffers
+    (``rpool_options.zero_fill_in_tail``; FusedStep: it is the forward launch).
     ``deterministic``: segmented reduction instead of atomics (bit-identical from run to
     run).  Its scratch holds one private window per RoI; without ``det_scratch`` (a uint8
     CUDA tensor) the exact size is computed on the device first, which synchronises the
@@ -357,6 +360,7 @@ def backward(plan, gys, deterministic=False, out=None, accumulate=False, check_f
         grads = user_out
     prob = _fill_problem(plan, [g.data_ptr() for g in grads], [g.data_ptr() for g in g_in],
                          accumulate=accumulate and not padded, deterministic=deterministic)
+    prob.opt.zero_fill_in_tail = int(bool(fill_in_tail))
     L = _lib.lib()
     with _on(plan.device):
         ws, ws_n = plan.workspace.data_ptr(), plan.workspace.numel()

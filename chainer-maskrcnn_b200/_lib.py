@@ -47,7 +47,8 @@ class Options(ctypes.Structure):
                 ("fuse_heads_backward", ctypes.c_int32),
                 ("prefetch_rows", ctypes.c_int32),
                 ("prefetch_rois", ctypes.c_int32),
-                ("reserved", ctypes.c_int32 * 2)]
+                ("zero_fill_in_tail", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
 
 
 OPTION_NAMES = tuple(n for n, _ in Options._fields_ if n != "reserved")

@@ -37,7 +37,8 @@ class FusedStep(object):
     gradient per pooled size (None: forward only)."""
 
     def __init__(self, features, rois, levels, spatial_scales, out_sizes, sampling_ratio=1,
-                 gys=None, graph=True, deterministic=False, fork_zero_fill=False, options=None):
+                 gys=None, graph=True, deterministic=False, fork_zero_fill=False, options=None,
+                 fill_in_tail=True):
         self.features = list(features)
         self.rois, self.levels = rois, levels
         self.scales = list(spatial_scales)
@@ -45,6 +46,7 @@ class FusedStep(object):
         self.sampling_ratio = int(sampling_ratio)
         self.gys = None if gys is None else list(gys)
         self.deterministic = bool(deterministic)
+        self.fill_in_tail = bool(fill_in_tail)
         self.options = dict(options or {})
         dev = rois.device
         for i, f in enumerate(self.features):
@@ -97,9 +99,12 @@ class FusedStep(object):
                     n = _engine.det_scratch_bytes(self.plan)
                     self._det_scratch = torch.empty(n + n // 4 + 4096, dtype=torch.uint8, device=dev)
                 # (no flag read-back inside the step: it would synchronise; see status_flags)
+                # the kernel queued before this call is the step's own forward launch, which does not
+                # touch the gradients: the zero fill may use its tail
                 _engine.backward(self.plan, self.gys, out=self.grads, accumulate=self.fork,
                                  deterministic=self.deterministic, check_flags=False,
-                                 det_scratch=self._det_scratch)
+                                 det_scratch=self._det_scratch,
+                                 fill_in_tail=self.fill_in_tail and not self.fork)
             if marks:
                 marks[2].record(cur)
 

@@ -25,7 +25,7 @@ constexpr int kMaxSmem = 227 * 1024;
 
 // rpool_options with the defaults filled in (0 = default in the ABI)
 struct Options {
-    int threads, order, force_path, split_heads, prefetch;
+    int threads, order, force_path, split_heads, prefetch, fill_in_tail;
 };
 // CTA size of the pooling kernels when opt.cta_threads is 0: 4 warps per RoI, 4 such CTAs resident
 // per SM (register-limited).  A problem that does not even fill one wave of those (148 SMs x 4) is
@@ -55,6 +55,29 @@ int cuda_fail(cudaError_t e, const char *what)
         cudaError_t e__ = (expr);                         \
         if (e__ != cudaSuccess) return cuda_fail(e__, what); \
     } while (0)
+
+// Launch that may start in the tail of the previous kernel of the stream (programmatic dependent
+// launch): once every CTA of that kernel has executed griddepcontrol.launch_dependents
+// (allow_dependents_early) or exited.  What the early kernel needs from its predecessors it must
+// wait for itself (wait_for_predecessors); a kernel launched normally after it still waits for
+// everything before it.
+template <typename... Params, typename... Args>
+cudaError_t launch_in_tail(void (*kern)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                           const Args &...args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, Params(args)...);
+}
 
 // workspace layout (r = R rounded up to 32, nb = key blocks of kKeyBlock RoIs):
 //   int32  levels[r] order[r] keys[r] rflags[r] gstart[288] bh[nb * 256] rects[4r]
@@ -127,13 +150,16 @@ int read_options(const rpool_problem *p, Options &o)
         return fail(RPOOL_ERR_INVALID, "opt.prefetch_rows=%d outside [-1,16]", q.prefetch_rows);
     if (q.prefetch_rois < 0 || q.prefetch_rois > 65536)
         return fail(RPOOL_ERR_INVALID, "opt.prefetch_rois=%d outside [0,65536]", q.prefetch_rois);
-    if (q.reserved[0] || q.reserved[1])
+    if (q.zero_fill_in_tail < 0 || q.zero_fill_in_tail > 1)
+        return fail(RPOOL_ERR_INVALID, "opt.zero_fill_in_tail=%d outside [0,1]", q.zero_fill_in_tail);
+    if (q.reserved)
         return fail(RPOOL_ERR_INVALID, "opt.reserved must be zero");
     o.threads = q.cta_threads ? q.cta_threads
                               : (p->n_rois <= kOneWaveRois ? kSmallProblemThreads : kDefaultThreads);
     o.order = q.schedule;
     o.force_path = q.force_path;
     o.split_heads = q.fuse_heads_backward ? 0 : 1;
+    o.fill_in_tail = q.zero_fill_in_tail;
     // kernel encoding: -1 off; -1-k row-ahead by k window rows; n >= 0 the whole RoI n slots later
     if (q.prefetch_rois > 0) o.prefetch = q.prefetch_rois - 1;
     else if (q.prefetch_rows < 0) o.prefetch = -1;
@@ -380,8 +406,15 @@ int rpool_plan(const rpool_problem *p, void *ws, size_t ws_size, void *stream)
     }
     KParams kp;
     fill_params(p, w, o, false, kPlanThreads, kp);
-    rpool_plan_kernel<<<(p->n_rois + kPlanWarps - 1) / kPlanWarps, kPlanThreads, 0, st>>>(kp, k, w.recs_fwd, w.recs_bwd);
-    CUDA_TRY(cudaGetLastError(), "rpool_plan_kernel launch");
+    const dim3 plan_grid((p->n_rois + kPlanWarps - 1) / kPlanWarps);
+    if (k.n_blocks > 0) {
+        // behind rpool_keys_kernel: starts in its shadow, builds the tables, waits before ranking
+        CUDA_TRY(launch_in_tail(rpool_plan_kernel, plan_grid, dim3(kPlanThreads), 0, st, kp, k, w.recs_fwd, w.recs_bwd),
+                 "rpool_plan_kernel launch");
+    } else {
+        rpool_plan_kernel<<<plan_grid, kPlanThreads, 0, st>>>(kp, k, w.recs_fwd, w.recs_bwd);
+        CUDA_TRY(cudaGetLastError(), "rpool_plan_kernel launch");
+    }
     g_launches++;
     return RPOOL_OK;
 }
@@ -402,8 +435,10 @@ int rpool_forward(const rpool_problem *p, void *ws, size_t ws_size, void *stream
                     smem, kMaxSmem);
     rc = set_smem(rpool_forward_kernel, 0, smem);
     if (rc) return rc;
-    rpool_forward_kernel<<<p->n_rois, threads, smem, static_cast<cudaStream_t>(stream)>>>(k);
-    CUDA_TRY(cudaGetLastError(), "rpool_forward_kernel launch");
+    // (always safe: the kernel's first instruction waits for everything queued before it; what the
+    // early start buys is the launch ramp, hidden in the plan kernel's tail)
+    CUDA_TRY(launch_in_tail(rpool_forward_kernel, dim3(p->n_rois), dim3(threads), (size_t)smem,
+                            static_cast<cudaStream_t>(stream), k), "rpool_forward_kernel launch");
     g_launches++;
     return RPOOL_OK;
 }
@@ -554,7 +589,7 @@ static int validate_levels(const rpool_problem *p)
     return RPOOL_OK;
 }
 
-static int launch_zero(const rpool_problem *p, cudaStream_t st)
+static int launch_zero(const rpool_problem *p, cudaStream_t st, bool in_tail)
 {
     ZeroParams z;
     memset(&z, 0, sizeof(z));
@@ -568,8 +603,14 @@ static int launch_zero(const rpool_problem *p, cudaStream_t st)
         if (z.tail[l] > 1024ull * 148 * 8)
             return fail(RPOOL_ERR_UNSUPPORTED, "level %d gradient is not 16-byte aligned", l);
     }
-    rpool_zero_kernel<<<148 * 8, 1024, 0, st>>>(z);
-    CUDA_TRY(cudaGetLastError(), "rpool_zero_kernel launch");
+    // 256-thread CTAs (18 registers): they fit beside the pooling CTAs that are still running when
+    // the fill starts in the tail of the previous launch (opt.zero_fill_in_tail)
+    if (in_tail) {
+        CUDA_TRY(launch_in_tail(rpool_zero_kernel, dim3(148 * 32), dim3(256), 0, st, z), "rpool_zero_kernel launch");
+    } else {
+        rpool_zero_kernel<<<148 * 32, 256, 0, st>>>(z);
+        CUDA_TRY(cudaGetLastError(), "rpool_zero_kernel launch");
+    }
     g_launches++;
     return RPOOL_OK;
 }
@@ -578,7 +619,9 @@ int rpool_zero_fill(const rpool_problem *p, void *stream)
 {
     int rc = validate_levels(p);
     if (rc) return rc;
-    return launch_zero(p, static_cast<cudaStream_t>(stream));
+    if (p->opt.zero_fill_in_tail < 0 || p->opt.zero_fill_in_tail > 1)
+        return fail(RPOOL_ERR_INVALID, "opt.zero_fill_in_tail=%d outside [0,1]", p->opt.zero_fill_in_tail);
+    return launch_zero(p, static_cast<cudaStream_t>(stream), p->opt.zero_fill_in_tail != 0);
 }
 
 int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *stream)
@@ -591,7 +634,7 @@ int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *strea
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (p->deterministic) return backward_det(p, ws, o, st);
     if (!p->accumulate) {
-        rc = launch_zero(p, st);
+        rc = launch_zero(p, st, o.fill_in_tail != 0);
         if (rc) return rc;
     }
     if (p->n_rois == 0) return RPOOL_OK;
@@ -620,8 +663,19 @@ int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *strea
         k.rec_stride = w.rec_stride;       // records keep the layout of the plan's head count
         rc = set_smem(rpool_backward_kernel, 1, smem);
         if (rc) return rc;
-        rpool_backward_kernel<<<p->n_rois, threads, smem, st>>>(k);
-        CUDA_TRY(cudaGetLastError(), "rpool_backward_kernel launch");
+        // the launch for the second pooled size depends on the zero fill only, like the first one:
+        // it may start in the first one's tail (both add into the gradients with reductions)
+        // ... and the first one, when this call's own zero fill is the kernel before it, may start in the
+        // fill's tail: it waits before its first reduction (what it reads earlier -- the plan, gy --
+        // was complete before the fill started, or is covered by opt.zero_fill_in_tail's contract)
+        k.wait_fill = (part == 0 && !p->accumulate) ? 1 : 0;
+        if (part > 0 || !p->accumulate) {
+            CUDA_TRY(launch_in_tail(rpool_backward_kernel, dim3(p->n_rois), dim3(threads), (size_t)smem, st, k),
+                     "rpool_backward_kernel launch");
+        } else {
+            rpool_backward_kernel<<<p->n_rois, threads, smem, st>>>(k);
+            CUDA_TRY(cudaGetLastError(), "rpool_backward_kernel launch");
+        }
         g_launches++;
     }
     return RPOOL_OK;

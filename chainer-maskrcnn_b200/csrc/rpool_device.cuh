@@ -65,6 +65,7 @@ struct KParams {
     int rec_stride;
     int rec_head;    // first head part of the stored record this launch uses (0 unless heads are split)
     int force_path;
+    int wait_fill;   // backward: this launch started in the zero fill's tail and must wait before it adds
 };
 
 // ---------------------------------------------------------------------------
@@ -332,6 +333,22 @@ __device__ __forceinline__ void stg128(float *p, float4 v)
     asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// Programmatic dependent launch: tells the scheduler that the NEXT kernel in the stream, when
+// it was launched with the programmatic-serialisation attribute, may start as soon as every CTA
+// of this grid has got here -- i.e. in this grid's tail, on the SMs that have run out of CTAs.
+// (No effect otherwise.)  Used where the next kernel does not read what this one writes.
+__device__ __forceinline__ void allow_dependents_early()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// The other half: a kernel that WAS launched early waits here until the kernels before it in the
+// stream have completed and their writes are visible (returns at once in a normal launch).
+__device__ __forceinline__ void wait_for_predecessors()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // bulk L2 prefetch through the TMA unit (bytes: multiple of 16)
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 {

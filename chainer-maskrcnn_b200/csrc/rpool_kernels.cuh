@@ -189,6 +189,7 @@ __device__ __noinline__ void generic_backward(const KParams &P)
     RoiCtx c;
     roi_prologue(P, c);
     if (!c.valid) return;
+    if (P.wait_fill) wait_for_predecessors();      // (see bwd_tasks: the gradients must be clean)
     const int C = P.C;
     const Strides4 fs = strides_of(P.feat_layout, C, c.L.H, c.L.W);
     float *grad = c.L.data + (long long)c.b * fs.s0;
@@ -389,6 +390,8 @@ rpool_forward_kernel(const __grid_constant__ KParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockCtl *ctl = reinterpret_cast<BlockCtl *>(smem_raw);
+    wait_for_predecessors();      // launched early, in the plan kernel's tail: the records must be there
+    allow_dependents_early();     // a zero fill queued behind this launch may use the tail
 
     load_record(P, ctl);
     RoiCtx c;
@@ -418,6 +421,17 @@ rpool_forward_kernel(const __grid_constant__ KParams P)
 // forward footprint table.  The gy bin rows a warp's next task is the first to need
 // are pulled into L2 with one bulk prefetch (TMA unit) per bin row while the column
 // pass of the current task runs.
+// A CTA of a launch that started in the zero fill's tail: wait for the fill (no-op when some warp
+// already did), then let the next launch go.  Every such CTA passes here before it exits, so the
+// next launch can never start adding before the fill is complete.
+__device__ __forceinline__ void bwd_release(const KParams &P)
+{
+    if (P.wait_fill) {
+        wait_for_predecessors();
+        allow_dependents_early();
+    }
+}
+
 struct TTab {
     int pa[kExt], pb[kExt];  // covering bin rows of window row i: [pa, pb)
 };
@@ -505,6 +519,7 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
     float *img = c.L.data + (size_t)c.b * c.L.H * c.L.W * C;
 
     const int ntask = Hc * slabs;
+    bool waited = false;
     for (int t = warp; t < ntask; t += nwarps) {
         const int i = t / slabs;
         const int ch = (t - i * slabs) * 128 + lane * 4;
@@ -603,6 +618,9 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
                 else bwd_col_pass<4>(G, cnt, wp, zp);
                 const unsigned m = ctl->hd[h].cmask[q];
                 if (det_win == nullptr) {
+                    // (launched early, in the zero fill's tail: everything up to here only read gy
+                    // and the plan; the gradients must be clean before the first reduction)
+                    if (P.wait_fill && !waited) { bwd_release(P); waited = true; }
                     float *gp = grow_img + (size_t)ctl->hd[h].cx0[q] * C;
 #pragma unroll
                     for (int s = 0; s < kSW; ++s)
@@ -632,6 +650,10 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockCtl *ctl = reinterpret_cast<BlockCtl *>(smem_raw);
+    // The launch for the next pooled size may use this one's tail.  It does not wait for anything
+    // itself, so when THIS launch started early (in the zero fill's tail, wait_fill) a CTA gives
+    // the signal only once it has seen the fill complete -- see bwd_release.
+    if (!P.wait_fill) allow_dependents_early();
     const int kCtlBytes = (rec_bytes(P.n_heads) + 127) & ~127;   // only this launch's head parts are loaded
     constexpr int kTTabBytes = (sizeof(TTab) + 127) & ~127;
     TTab *tt = reinterpret_cast<TTab *>(smem_raw + kCtlBytes);
@@ -657,7 +679,7 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     load_record(P, ctl);
     RoiCtx c;
     ctx_from_record(P, ctl, c);
-    if (!c.valid) return;
+    if (!c.valid) { bwd_release(P); return; }
     const int need = kRecShape | kRecFits;
     bool table_ok = (ctl->flags & need) == need && P.force_path != kPathGeneric && pointers_aligned(P, c.L);
     for (int h = 0; h < P.n_heads; ++h) table_ok = table_ok && P.PH[h] <= kPBwd && P.PW[h] <= kPBwd;
@@ -666,9 +688,10 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     if (!table_ok || y1 - y0 >= kExt) {
         if (P.det) { if (threadIdx.x == 0) atomicExch(P.det_err, 1); }   // no ordered generic path
         else generic_backward(P);
+        bwd_release(P);
         return;
     }
-    if (x1 < x0 || y1 < y0) return;
+    if (x1 < x0 || y1 < y0) { bwd_release(P); return; }
     float *det_win = nullptr;
     if (P.det) {
         // this RoI's private window in the scratch buffer: zero it, then the tasks
@@ -711,6 +734,7 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     for (int h = 0; h < P.n_heads; ++h) exact = exact && (P.PW[h] % kZ == 0);
     if (exact) bwd_tasks<256, true>(P, c, ctl, tt, strip, det_win);
     else bwd_tasks<0, false>(P, c, ctl, tt, strip, det_win);
+    bwd_release(P);
 }
 
 // ---------------------------------------------------------------------------
@@ -796,6 +820,7 @@ __device__ __forceinline__ int plan_key(const PlanParams &p, int i, int &lvl_out
 __global__ void __launch_bounds__(kKeyBlock)
 rpool_keys_kernel(const __grid_constant__ PlanParams p)
 {
+    allow_dependents_early();     // the plan kernel builds its tables meanwhile and waits before ranking
     __shared__ int hist[kPlanMaxKeys];
     const int tid = threadIdx.x;
     for (int k = tid; k < p.K; k += kKeyBlock) hist[k] = 0;
@@ -935,6 +960,40 @@ rpool_plan_kernel(const __grid_constant__ KParams P, const __grid_constant__ Pla
         __syncthreads();
     }
 
+    // ---- the RoI's record for the forward geometry, built before anything of rpool_keys_kernel is
+    // read: in two-launch mode this kernel starts in that kernel's shadow
+    const bool mine = i < p.R;
+    int lvl = 0, fl = 0, key = 0;
+    BlockCtl *ctl = &ctl_s[warp];
+    RoiCtx c;
+    const int n16 = rec_bytes(P.n_heads) >> 4;
+    const int n_sets = recs_bwd != recs_fwd ? 2 : 1;
+    auto build = [&](int bwd) {
+        __syncwarp();    // the previous set has left shared memory
+        if (lane == 0) {
+            ctl->r = c.r; ctl->lvl = c.lvl; ctl->b = c.b;
+            ctl->flags = (c.valid ? kRecValid : 0) | (c.fast_ok ? kRecShape : 0) | kRecFits;
+        }
+        __syncwarp();
+        if (c.valid && c.fast_ok) {      // (uniform) otherwise the consumer takes the generic path
+            warp_build_tables(P, c, bwd != 0, ctl, lane);
+            if (ctl->flags & kRecFits) warp_build_chunks(P, c, ctl, kPMax, lane);
+        }
+        __syncwarp();
+    };
+    if (mine) {
+        key = plan_key(p, i, lvl, fl);
+        c.r = i;
+        c.lvl = lvl;
+        c.L = P.lvl[lvl];
+        c.box = load_roi(P.rois, i, P.roi_format);
+        c.b = c.box.b;
+        c.valid = (c.b >= 0 && c.b < c.L.n_images);
+        c.fast_ok = shapes_allow_tables(P, c.L);
+        build(0);
+    }
+    wait_for_predecessors();      // rpool_keys_kernel's keys and histograms from here on
+
     // ---- gstart: first slot of every key (CTA 0, all its warps)
     if (first && p.gstart) {
         for (int k = tid; k <= kPlanMaxKeys; k += kPlanThreads) s_hist[k] = 0;
@@ -959,11 +1018,9 @@ rpool_plan_kernel(const __grid_constant__ KParams P, const __grid_constant__ Pla
             *p.det_err = 0;
         }
     }
-    if (i >= p.R) return;
+    if (!mine) return;
 
     // ---- slot of RoI i: stable rank of (key_i, i)
-    int lvl, fl;
-    const int key = plan_key(p, i, lvl, fl);
     int slot = i;
     if (p.order_mode != RPOOL_SCHED_INPUT) {
         int acc = 0;
@@ -989,30 +1046,8 @@ rpool_plan_kernel(const __grid_constant__ KParams P, const __grid_constant__ Pla
         p.order[slot] = i;
         p.rflags[i] = fl;
     }
-
-    // ---- the RoI's record(s)
-    BlockCtl *ctl = &ctl_s[warp];
-    RoiCtx c;
-    c.r = i;
-    c.lvl = lvl;
-    c.L = P.lvl[lvl];
-    c.box = load_roi(P.rois, i, P.roi_format);
-    c.b = c.box.b;
-    c.valid = (c.b >= 0 && c.b < c.L.n_images);
-    c.fast_ok = shapes_allow_tables(P, c.L);
-    const int n16 = rec_bytes(P.n_heads) >> 4;
-    for (int bwd = 0; bwd < (recs_bwd != recs_fwd ? 2 : 1); ++bwd) {
-        __syncwarp();    // the previous set has left shared memory
-        if (lane == 0) {
-            ctl->r = c.r; ctl->lvl = c.lvl; ctl->b = c.b;
-            ctl->flags = (c.valid ? kRecValid : 0) | (c.fast_ok ? kRecShape : 0) | kRecFits;
-        }
-        __syncwarp();
-        if (c.valid && c.fast_ok) {      // (uniform) otherwise the consumer takes the generic path
-            warp_build_tables(P, c, bwd != 0, ctl, lane);
-            if (ctl->flags & kRecFits) warp_build_chunks(P, c, ctl, kPMax, lane);
-        }
-        __syncwarp();
+    for (int bwd = 0; bwd < n_sets; ++bwd) {
+        if (bwd) build(bwd);
         const uint4 *src = reinterpret_cast<const uint4 *>(ctl);
         uint4 *dst = reinterpret_cast<uint4 *>((bwd ? recs_bwd : recs_fwd) + (size_t)slot * P.rec_stride);
         for (int k = lane; k < n16; k += 32) dst[k] = src[k];
@@ -1256,6 +1291,8 @@ struct ZeroParams {
 };
 __global__ void rpool_zero_kernel(const __grid_constant__ ZeroParams p)
 {
+    allow_dependents_early();     // the backward launch queued behind the fill loads its records and
+                                  // gy rows meanwhile and waits before its first reduction
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     const unsigned long long t0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -106,7 +106,13 @@ typedef struct rpool_options {
                              * 0 = default (2), -1 = off, 1..16 */
     int32_t prefetch_rois;  /* backward, rows variant: > 0 replaces the row-ahead prefetch by the whole
                              * RoI of the CTA scheduled prefetch_rois - 1 slots later */
-    int32_t reserved[2];    /* must be zero */
+    int32_t zero_fill_in_tail; /* rpool_backward / rpool_zero_fill: 1 = the zero fill may start while the
+                             * kernel queued before it on the stream is still draining (programmatic
+                             * dependent launch).  The CALLER guarantees that that kernel neither touches
+                             * the gradient buffers nor produces the upstream gradients -- e.g. it is this
+                             * problem's rpool_forward, as in the step helper of the Python package.
+                             * 0 = plain stream order */
+    int32_t reserved;       /* must be zero */
 } rpool_options;
 
 /* One pyramid level.  `data` is the feature map in rpool_forward (read) and
