@@ -829,12 +829,18 @@ def run_b200(args):
                          "frac": frac(step_bytes, step_ms),
                          "frac_of_nominal_8TBps": step_bytes / (step_ms * 1e-3) / 1e9 / 8000.0},
         "launched_from_python": {"ms_per_step": launched_ms, "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
-                                 "frac": frac(step_bytes, launched_ms)},
-        "serial_r01_sequence": {"ms_per_step": s_tot, "fwd_ms": s_fwd, "bwd_ms": s_bwd,
-                                "frac": frac(step_bytes, s_tot), "bwd_pair_frac": frac(ab["bwd"], s_bwd),
-                                "what": "plan, forward, zero fill, backward one after the other on one "
-                                        "stream, launched from Python (the r01 step)"},
+                                 "frac": frac(step_bytes, launched_ms),
+                                 "what": "the same step launched from Python, CUDA events after the plan + forward "
+                                         "launches and after the backward launches: where fwd_ms / bwd_ms and the "
+                                         "per-launch figures above come from"},
+        "overlap": "the replayed step is shorter than the sum of its launches: the zero fill starts in the "
+                   "forward's tail, the plan in the keys kernel's shadow, the forward in the plan's tail and the "
+                   "backward launches in the fill's / each other's tail (programmatic dependent launches)",
     }
+    if forked:
+        roofline["serial_sequence"] = {"ms_per_step": s_tot, "fwd_ms": s_fwd, "bwd_ms": s_bwd,
+                                       "frac": frac(step_bytes, s_tot), "bwd_pair_frac": frac(ab["bwd"], s_bwd),
+                                       "what": "the same step without the forked fill, launched from Python"}
     parity = None
     if world == 1 and not args.no_parity:
         try:

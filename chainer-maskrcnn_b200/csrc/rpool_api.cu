@@ -465,11 +465,19 @@ static int det_prepass(const rpool_problem *p, void *ws, const Options &o, cudaS
     k.reverse = 0;
     CUDA_TRY(cudaMemsetAsync(w.det_err, 0, sizeof(int), st), "cudaMemsetAsync(det_err)");
     if (p->n_rois > 0) {
-        rpool_det_rects_kernel<<<(p->n_rois + 127) / 128, 128, 0, st>>>(k, w.rects, w.sizes, w.det_err);
-        CUDA_TRY(cudaGetLastError(), "rpool_det_rects_kernel launch");
-        rpool_det_scan_kernel<<<1, 1024, 0, st>>>(w.order, w.sizes, p->n_rois, w.woff, w.det_total);
+        ScanParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.recs = w.recs_bwd;
+        sp.rec_stride = w.rec_stride;
+        sp.R = p->n_rois;
+        sp.C = p->channels;
+        sp.shapes_ok = o.force_path != kPathGeneric;
+        for (int h = 0; h < p->n_heads; ++h)
+            sp.shapes_ok = sp.shapes_ok && p->out_h[h] <= kPBwd && p->out_w[h] <= kPBwd;
+        sp.rects = w.rects; sp.woff = w.woff; sp.total = w.det_total; sp.err = w.det_err;
+        rpool_det_scan_kernel<<<1, 1024, 0, st>>>(sp);
         CUDA_TRY(cudaGetLastError(), "rpool_det_scan_kernel launch");
-        g_launches += 2;
+        g_launches++;
     } else {
         CUDA_TRY(cudaMemsetAsync(w.det_total, 0, sizeof(unsigned long long), st), "cudaMemsetAsync(det_total)");
     }
@@ -547,13 +555,17 @@ static int backward_det(const rpool_problem *p, void *ws, const Options &o, cuda
     GatherParams g;
     memset(&g, 0, sizeof(g));
     long long ctas = 0;
-    for (int l = 0; l < p->n_levels; ++l) {
+    for (int li = 0; li < p->n_levels; ++li) {
+        const int l = p->n_levels - 1 - li;       // launch order: coarse levels first
         g.lvl[l].data = static_cast<float *>(p->level[l].data);
         g.lvl[l].n_images = p->level[l].n_images;
         g.lvl[l].H = p->level[l].height;
         g.lvl[l].W = p->level[l].width;
-        g.strips[l] = (p->level[l].width + kGatherCells - 1) / kGatherCells;
-        g.strip_base[l] = ctas;
+        // at most 8 CTAs per map row: strips of 8, 16, 24 ... cells
+        const int groups = (p->level[l].width + kGatherWarps - 1) / kGatherWarps;
+        g.cells[l] = kGatherWarps * ((groups + 7) / 8);
+        g.strips[l] = (p->level[l].width + g.cells[l] - 1) / g.cells[l];
+        g.strip_base[li] = ctas;
         ctas += (long long)p->level[l].n_images * p->level[l].height * g.strips[l];
     }
     g.strip_base[p->n_levels] = ctas;
@@ -561,13 +573,14 @@ static int backward_det(const rpool_problem *p, void *ws, const Options &o, cuda
     g.n_levels = p->n_levels;
     g.C = p->channels;
     g.accumulate = p->accumulate;
-    g.order = w.order; g.gstart = w.gstart; g.rects = w.rects; g.woff = w.woff;
+    g.gstart = w.gstart; g.rects = w.rects; g.woff = w.woff;
     g.scratch = static_cast<const float *>(p->det_workspace);
     if (p->n_rois == 0) {
         // no plan was made: every group is empty
         CUDA_TRY(cudaMemsetAsync(w.gstart, 0, kGstartInts * sizeof(int), st), "cudaMemsetAsync(gstart)");
     }
-    rpool_det_gather_kernel<<<(unsigned)ctas, kGatherCells * 32, 0, st>>>(g);
+    if (p->channels <= 256) rpool_det_gather_kernel<2><<<(unsigned)ctas, kGatherWarps * 32, 0, st>>>(g);
+    else rpool_det_gather_kernel<kGatherSlabs><<<(unsigned)ctas, kGatherWarps * 32, 0, st>>>(g);
     CUDA_TRY(cudaGetLastError(), "rpool_det_gather_kernel launch");
     g_launches++;
     return RPOOL_OK;

@@ -526,6 +526,7 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
         const bool active = kExact || ch < C;
         float *grow_img = img + (size_t)(y0 + i) * c.L.W * C + ch;   // column 0 of the window row
         bool ahead_done = false;
+        unsigned long long wrote = 0;      // deterministic: window columns of this row already stored
         auto row_ahead = [&]() {
             if (P.prefetch <= -2 && lane == 0 && t - i * slabs == 0) {
                 // row-ahead mode: pull the gy bin rows that window row i + lead is the first to
@@ -626,21 +627,35 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
                     for (int s = 0; s < kSW; ++s)
                         if (active && ((m >> s) & 1u)) red_add_v4(gp + (kC ? s * kC : s * C), G[s]);
                 } else {
-                    // deterministic: plain read-modify-write of this RoI's private window
-                    // (this warp is the only writer of its row and slab; heads in order)
-                    float *gp = det_win + ((size_t)i * det_wc + (ctl->hd[h].cx0[q] - x0)) * C + ch;
+                    // deterministic: this RoI's private window (this warp is the only writer of its
+                    // row and slab; heads and chunks in order).  The first contribution to a cell is a
+                    // plain store, later ones (chunk overlaps, the second pooled size) read-modify-write;
+                    // windows wider than 64 columns were zero-filled and always read-modify-write.
+                    const int col0 = ctl->hd[h].cx0[q] - x0;
+                    float *gp = det_win + ((size_t)i * det_wc + col0) * C + ch;
 #pragma unroll
                     for (int s = 0; s < kSW; ++s) {
                         if (active && ((m >> s) & 1u)) {
                             float *a = gp + (kC ? s * kC : s * C);
-                            float4 v = ldg_cg128(a);
-                            v.x += G[s].x; v.y += G[s].y; v.z += G[s].z; v.w += G[s].w;
+                            float4 v = G[s];
+                            if (det_wc > 64 || ((wrote >> (col0 + s)) & 1ull)) {
+                                const float4 o = ldg_cg128(a);
+                                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                            }
                             stg128(a, v);
                         }
                     }
+                    // (a span starts left of the window when the window touches the map's right edge)
+                    if (det_wc <= 64) wrote |= col0 >= 0 ? (unsigned long long)m << col0 : (unsigned long long)m >> -col0;
                 }
             }
             __syncwarp();
+        }
+        if (det_win != nullptr && det_wc <= 64 && active) {
+            // deterministic: the cells of this window row that received nothing
+            float *gp = det_win + (size_t)i * det_wc * C + ch;
+            for (int col = 0; col < det_wc; ++col)
+                if (!((wrote >> col) & 1ull)) stg128(gp + (size_t)col * C, make_float4(0.f, 0.f, 0.f, 0.f));
         }
     }
 }
@@ -696,16 +711,17 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     if (P.det) {
         // this RoI's private window in the scratch buffer: zero it, then the tasks
         // below add into it with plain stores
-        const int *rc = P.det_rects + 4 * (size_t)c.r;
-        const unsigned long long off = P.det_woff[c.r];
+        const int *rc = P.det_rects + 4 * (size_t)launch_slot(P);
+        const unsigned long long off = P.det_woff[launch_slot(P)];
         const unsigned long long n = (unsigned long long)(x1 - x0 + 1) * (y1 - y0 + 1) * P.C;
         if (rc[0] != x0 || rc[1] != y0 || rc[2] != x1 || rc[3] != y1 || off + n > P.det_scratch_floats) {
             if (threadIdx.x == 0) atomicExch(P.det_err, 2);
             return;
         }
         det_win = P.det_scratch + off;
-        for (unsigned long long i = threadIdx.x * 4ull; i < n; i += blockDim.x * 4ull)
-            stg128(det_win + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        if (x1 - x0 + 1 > 64)      // (narrower windows: first-touch stores, see bwd_tasks)
+            for (unsigned long long i = threadIdx.x * 4ull; i < n; i += blockDim.x * 4ull)
+                stg128(det_win + i, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     build_ttabs(P, ctl, tt);
     if (P.prefetch <= -2 && P.pool_layout == RPOOL_NHWC && (P.C & 3) == 0) {
@@ -1096,66 +1112,53 @@ __global__ void rpool_levels_kernel(const __grid_constant__ LevelParams p)
 // ---------------------------------------------------------------------------
 // deterministic backward: segmented reduction instead of atomics
 // ---------------------------------------------------------------------------
-// 1. rpool_det_rects_kernel   window rectangle of every RoI (same footprint
-//                             arithmetic as the pooling kernels) and its size;
-// 2. rpool_det_scan_kernel    exclusive scan of the sizes in schedule order ->
-//                             offset of each RoI's private window in the scratch;
-// 3. rpool_backward_kernel    (det = 1) writes each RoI's window contribution to
-//                             its private window: plain stores, one writer per cell;
-// 4. rpool_det_gather_kernel  every feature cell sums, in schedule order, the
-//                             windows that cover it and is written exactly once
-//                             (this also replaces the zero fill).
+// 1. rpool_det_scan_kernel    window rectangle of every RoI (from its record's header) and an
+//                             exclusive scan of the window sizes in schedule order -> offset
+//                             of each RoI's private window in the scratch;
+// 2. rpool_backward_kernel    (det = 1) writes each RoI's window contribution to its private
+//                             window: one writer per cell, the first contribution a plain store;
+// 3. rpool_det_gather_kernel  every feature cell sums, in schedule order, the windows that
+//                             cover it (four windows' loads in flight at a time) and is written
+//                             exactly once (this also replaces the zero fill).
 // The summation order of every cell is fixed by the schedule, so results are
 // bit-identical from run to run.
-__global__ void rpool_det_rects_kernel(const __grid_constant__ KParams P, int *rects,
-                                       unsigned long long *sizes, int *err)
-{
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= P.R) return;
-    RoiCtx c;
-    roi_decode(P, slot, c);
-    int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -1, y1 = -1;
-    bool ok = c.fast_ok && P.force_path != kPathGeneric;
-    for (int h = 0; h < P.n_heads; ++h) ok = ok && P.PH[h] <= kPBwd && P.PW[h] <= kPBwd;
-    if (c.valid && ok) {
-        for (int h = 0; h < P.n_heads; ++h) {
-            for (int axis = 0; axis < 2; ++axis) {
-                const AxisGeom g = axis_of(P, c, true, h, axis);
-                const int n_bins = axis ? P.PW[h] : P.PH[h];
-                for (int p = 0; p < n_bins; ++p) {
-                    int lo, n;
-                    float w[kNT];
-                    ok = axis_footprint(g, P.mode, p, lo, n, w) && ok;
-                    if (n > 0) {
-                        if (axis) { x0 = lo < x0 ? lo : x0; x1 = lo + n - 1 > x1 ? lo + n - 1 : x1; }
-                        else { y0 = lo < y0 ? lo : y0; y1 = lo + n - 1 > y1 ? lo + n - 1 : y1; }
-                    }
-                }
-            }
-        }
-        ok = ok && (y1 - y0 < kExt);
-    }
-    unsigned long long n = 0;
-    if (c.valid && !ok) atomicExch(err, 1);   // this RoI needs the generic path: not orderable
-    if (c.valid && ok && x1 >= x0 && y1 >= y0) n = (unsigned long long)(x1 - x0 + 1) * (y1 - y0 + 1) * P.C;
-    else { x0 = y0 = 0; x1 = y1 = -1; }
-    int *rc = rects + 4 * (size_t)c.r;
-    rc[0] = x0; rc[1] = y0; rc[2] = x1; rc[3] = y1;
-    sizes[slot] = n;
-}
+struct ScanParams {
+    const unsigned char *recs;   // per-slot records (backward geometry): the window extent is in the header
+    int rec_stride;
+    int R, C;
+    int shapes_ok;               // pooled sizes within the backward table path, table path not disabled
+    int *rects;                  // out, per slot: x0, y0, x1, y1
+    unsigned long long *woff;    // out, per slot: float offset of its private window
+    unsigned long long *total;   // out: floats of scratch needed
+    int *err;
+};
 
 __global__ void __launch_bounds__(1024)
-rpool_det_scan_kernel(const int *__restrict__ order, const unsigned long long *__restrict__ sizes, int R,
-                      unsigned long long *woff, unsigned long long *total)
+rpool_det_scan_kernel(const __grid_constant__ ScanParams p)
 {
     __shared__ unsigned long long wsum[32];
     __shared__ unsigned long long carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < R; base += 1024) {
-        const int i = base + tid;
-        const unsigned long long v = i < R ? sizes[i] : 0ull;
+    for (int base = 0; base < p.R; base += 1024) {
+        const int slot = base + tid;
+        unsigned long long v = 0ull;
+        if (slot < p.R) {
+            const int4 a = __ldg(reinterpret_cast<const int4 *>(p.recs + (size_t)slot * p.rec_stride));
+            const int4 f = __ldg(reinterpret_cast<const int4 *>(p.recs + (size_t)slot * p.rec_stride) + 1);
+            // a = wmin[0] (y0), wmin[1] (x0), wmax[0] (y1), wmax[1] (x1);  f = r, lvl, b, flags
+            const bool valid = (f.w & kRecValid) != 0;
+            const bool ok = p.shapes_ok && (f.w & (kRecShape | kRecFits)) == (kRecShape | kRecFits) &&
+                            a.z - a.x < kExt;
+            if (valid && !ok) atomicExch(p.err, 1);   // this RoI needs the generic path: not orderable
+            int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
+            if (valid && ok && a.w >= a.y && a.z >= a.x) {
+                x0 = a.y; y0 = a.x; x1 = a.w; y1 = a.z;
+                v = (unsigned long long)(x1 - x0 + 1) * (y1 - y0 + 1) * p.C;
+            }
+            *reinterpret_cast<int4 *>(p.rects + 4 * (size_t)slot) = make_int4(x0, y0, x1, y1);
+        }
         unsigned long long x = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -1175,108 +1178,137 @@ rpool_det_scan_kernel(const int *__restrict__ order, const unsigned long long *_
         }
         __syncthreads();
         const unsigned long long before = carry + (warp ? wsum[warp - 1] : 0ull) + x - v;
-        if (i < R) woff[order[i]] = before;
+        if (slot < p.R) p.woff[slot] = before;
         __syncthreads();
         if (tid == 0) carry += wsum[31];
         __syncthreads();
     }
-    if (tid == 0) *total = carry;
+    if (tid == 0) *p.total = carry;
 }
 
 struct GatherParams {
     LevelDev lvl[kMaxLevels];
-    long long strip_base[kMaxLevels + 1];  // first CTA of every level
-    int strips[kMaxLevels];                // 8-cell strips per map row
+    long long strip_base[kMaxLevels + 1];  // first CTA of every level, in launch order (coarse first)
+    int strips[kMaxLevels];                // CTAs per map row
+    int cells[kMaxLevels];                 // cells per CTA (a multiple of kGatherWarps)
     int n_levels, C, accumulate;
-    const int *order, *gstart, *rects;
-    const unsigned long long *woff;
+    const int *gstart;                     // first slot of every (image, level) group
+    const int *rects;                      // per slot: x0, y0, x1, y1 of the RoI's window
+    const unsigned long long *woff;        // per slot: float offset of its private window
     const float *scratch;
 };
 
-constexpr int kGatherCells = 8;   // cells (warps) per CTA
-constexpr int kGatherSlabs = 4;   // 128-channel slabs held in registers: C <= 512
+constexpr int kGatherWarps = 8;       // cells in flight per CTA
+constexpr int kGatherList = 1024;     // windows a CTA lists per pass
+constexpr int kGatherSlabs = 4;       // 128-channel slabs held in registers: C <= 512
 
-__global__ void __launch_bounds__(kGatherCells * 32)
+// One CTA per strip of a map row (a few CTAs per row: wide strips on the fine levels, where most
+// cells are covered by nothing and the CTA's fixed cost would otherwise dominate).  The CTA lists,
+// in schedule order, the windows of its (image, level) group that meet the strip (one coalesced
+// 16-byte load per slot, ordered compaction); its warps then take the strip's cells one by one.
+template <int kSlabs>
+__global__ void __launch_bounds__(kGatherWarps * 32)
 rpool_det_gather_kernel(const __grid_constant__ GatherParams p)
 {
-    __shared__ int s_x0[256], s_x1[256], s_y0[256], s_wc[256];
-    __shared__ unsigned long long s_off[256];
-    __shared__ int s_wcount[8], s_n;
+    __shared__ int s_x0[kGatherList], s_x1[kGatherList], s_y0[kGatherList], s_wc[kGatherList];
+    __shared__ unsigned long long s_off[kGatherList];
+    __shared__ int s_wcount[kGatherWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int l = 0;
-    while (l + 1 < p.n_levels && (long long)blockIdx.x >= p.strip_base[l + 1]) ++l;
+    // coarse levels come first in the launch: their strips meet the most windows (the longest CTAs)
+    int li = 0;
+    while (li + 1 < p.n_levels && (long long)blockIdx.x >= p.strip_base[li + 1]) ++li;
+    const int l = p.n_levels - 1 - li;
     const LevelDev L = p.lvl[l];
-    long long idx = (long long)blockIdx.x - p.strip_base[l];
+    long long idx = (long long)blockIdx.x - p.strip_base[li];
     const int sx = (int)(idx % p.strips[l]);
     idx /= p.strips[l];
     const int y = (int)(idx % L.H);
     const int b = (int)(idx / L.H);
-    const int xs = sx * kGatherCells, x = xs + warp;
+    const int xs = sx * p.cells[l];
+    int xe = xs + p.cells[l] - 1;
+    xe = xe < L.W - 1 ? xe : L.W - 1;
     const int key = b * p.n_levels + l;
     const int g0 = p.gstart[key], g1 = p.gstart[key + 1];
     const int C = p.C;
 
-    float4 acc[kGatherSlabs];
+    int next = g0;
+    bool more = true;
+    for (int pass = 0; more; ++pass) {
+        // ---- list the next windows (at most kGatherList) that meet this strip, in schedule order
+        int n = 0;
+        while (next < g1 && n + kGatherWarps * 32 <= kGatherList) {
+            const int slot = next + tid;
+            bool hit = false;
+            int4 rc = make_int4(0, 0, -1, -1);
+            if (slot < g1) {
+                rc = __ldg(reinterpret_cast<const int4 *>(p.rects) + slot);
+                hit = rc.y <= y && y <= rc.w && rc.x <= xe && rc.z >= xs;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_wcount[warp] = __popc(m);
+            __syncthreads();
+            int pos = n + __popc(m & ((1u << lane) - 1u));
+            int total = 0;
+            for (int w = 0; w < kGatherWarps; ++w) {
+                if (w < warp) pos += s_wcount[w];
+                total += s_wcount[w];
+            }
+            if (hit) {
+                s_x0[pos] = rc.x; s_x1[pos] = rc.z; s_y0[pos] = rc.y; s_wc[pos] = rc.z - rc.x + 1;
+                s_off[pos] = __ldg(p.woff + slot);
+            }
+            n += total;
+            next += kGatherWarps * 32;
+            __syncthreads();
+        }
+        more = next < g1;
+        // ---- the strip's cells
+        for (int x = xs + warp; x <= xe; x += kGatherWarps) {
+            float *dst = L.data + (((size_t)b * L.H + y) * L.W + x) * C + lane * 4;
+            float4 acc[kSlabs];
 #pragma unroll
-    for (int k = 0; k < kGatherSlabs; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    for (int batch = g0; batch < g1; batch += 256) {
-        // ordered compaction of the RoIs of this (image, level) whose window meets the strip
-        const int slot = batch + tid;
-        bool hit = false;
-        int rx0 = 0, rx1 = -1, ry0 = 0, ry1 = -1, r = 0;
-        if (slot < g1) {
-            r = p.order[slot];
-            const int4 rc = *reinterpret_cast<const int4 *>(p.rects + 4 * (size_t)r);
-            rx0 = rc.x; ry0 = rc.y; rx1 = rc.z; ry1 = rc.w;
-            hit = ry0 <= y && y <= ry1 && rx0 <= xs + kGatherCells - 1 && rx1 >= xs;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) s_wcount[warp] = __popc(m);
-        __syncthreads();
-        int pos = __popc(m & ((1u << lane) - 1u));
-        for (int w = 0; w < warp; ++w) pos += s_wcount[w];
-        if (hit) {
-            s_x0[pos] = rx0; s_x1[pos] = rx1; s_y0[pos] = ry0; s_wc[pos] = rx1 - rx0 + 1;
-            s_off[pos] = p.woff[r];
-        }
-        if (tid == 0) {
-            int n = 0;
-            for (int w = 0; w < kGatherCells; ++w) n += s_wcount[w];
-            s_n = n;
-        }
-        __syncthreads();
-        const int n = s_n;
-        if (x < L.W) {
-            for (int e = 0; e < n; ++e) {
-                if (s_x0[e] <= x && x <= s_x1[e]) {
-                    const float *src = p.scratch + s_off[e] +
-                                       ((size_t)(y - s_y0[e]) * s_wc[e] + (x - s_x0[e])) * C + lane * 4;
+            for (int k = 0; k < kSlabs; ++k) {
+                acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((pass > 0 || p.accumulate) && k * 128 + lane * 4 < C)
+                    acc[k] = *reinterpret_cast<const float4 *>(dst + k * 128);
+            }
+            // 32 list entries at a time: a lane tests one and works out where this cell lies in that
+            // window; the hits are then taken four at a time -- all their loads in flight together --
+            // and added in list (= schedule) order
+            for (int e0 = 0; e0 < n; e0 += 32) {
+                const int e = e0 + lane;
+                const bool cov = e < n && s_x0[e] <= x && x <= s_x1[e];
+                unsigned long long mine = 0ull;
+                if (cov) mine = s_off[e] + ((unsigned long long)(y - s_y0[e]) * s_wc[e] + (x - s_x0[e])) * C;
+                unsigned hits = __ballot_sync(0xffffffffu, cov);
+                while (hits) {
+                    float4 v[4][kSlabs];
 #pragma unroll
-                    for (int k = 0; k < kGatherSlabs; ++k) {
-                        if (k * 128 + lane * 4 < C) {
-                            const float4 v = ldg_nc128(src + k * 128);
-                            acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+                    for (int u = 0; u < 4; ++u) {
+                        const int src_lane = hits ? __ffs(hits) - 1 : 0;
+                        const bool on = hits != 0;
+                        hits &= hits - 1;
+                        const unsigned long long off = __shfl_sync(0xffffffffu, mine, src_lane);
+                        const float *src = p.scratch + off + lane * 4;
+#pragma unroll
+                        for (int k = 0; k < kSlabs; ++k) {
+                            v[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (on && k * 128 + lane * 4 < C) v[u][k] = ldg_nc128(src + k * 128);
                         }
                     }
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (x < L.W) {
-        float *dst = L.data + (((size_t)b * L.H + y) * L.W + x) * C + lane * 4;
 #pragma unroll
-        for (int k = 0; k < kGatherSlabs; ++k) {
-            if (k * 128 + lane * 4 < C) {
-                float4 v = acc[k];
-                if (p.accumulate) {
-                    const float4 o = *reinterpret_cast<const float4 *>(dst + k * 128);
-                    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int k = 0; k < kSlabs; ++k) {
+                            acc[k].x += v[u][k].x; acc[k].y += v[u][k].y; acc[k].z += v[u][k].z; acc[k].w += v[u][k].w;
+                        }
                 }
-                stg128(dst + k * 128, v);
             }
+#pragma unroll
+            for (int k = 0; k < kSlabs; ++k)
+                if (k * 128 + lane * 4 < C) stg128(dst + k * 128, acc[k]);
         }
+        __syncthreads();       // the list is consumed before the next pass overwrites it
     }
 }
 

@@ -1,12 +1,13 @@
-timeout 900 python -m pytest tests -m gpu -x -q -k "not full_size and not train_step and not fuzz" 2>&1 | tail -4
-for c in 13 1 3 0; do for o in "" "--no-tail"; do
-python bench.py --config $c --steps 30 --warmup 5 --no-e2e --no-cpu-baseline --no-gpu-baseline --no-parity $o > gpurun_out/r02m_tmp.json 2> gpurun_out/r02m_tmp.err
+timeout 900 python -m pytest tests -m gpu -x -q -k "deterministic or fuzz or accumulates or fused_step" 2>&1 | tail -5
+python bench.py --steps 20 --warmup 5 --deterministic --no-e2e --no-cpu-baseline --no-gpu-baseline > gpurun_out/r02_bench_det.json 2> gpurun_out/r02_bench_det.err
+python -c "
+import json; d=json.loads(open('gpurun_out/r02_bench_det.json').read().strip().splitlines()[-1]); print('det', d['ms_per_step'], d['fwd_ms'], d['bwd_ms'], d['parity']['ok'], d['parity']['backward'])"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r02_det_launches.csv python bench.py --steps 2 --warmup 1 --deterministic --no-e2e --no-cpu-baseline --no-gpu-baseline --no-parity --no-graph > /dev/null 2>&1
 python - <<P
-import json
-try:
-    d=json.loads(open("gpurun_out/r02m_tmp.json").read().strip().splitlines()[-1])
-    print("cfg$c [$o] step %.4f ms (frac %.3f) | launched %.4f: fwd %.4f bwd %.4f" % (d["ms_per_step"], d["roofline"]["fwd_plus_bwd"]["frac"], d["roofline"]["launched_from_python"]["ms_per_step"], d["fwd_ms"], d["bwd_ms"]))
-except Exception as e:
-    print("cfg$c [$o] FAILED", e); print(open("gpurun_out/r02m_tmp.err").read()[-1500:])
+import csv
+rows=list(csv.reader(l for l in open('gpurun_out/r02_det_launches.csv') if l.startswith('"')))
+h=rows[0]; ki=h.index("Kernel Name"); vi=h.index("Metric Value")
+print([(r[ki].split('(')[0].replace('rpool::rpool_','')[:20], float(r[vi])/1000) for r in rows[1:] if 'rpool' in r[ki]][-8:])
 P
-done; done
+for c in 3 0; do python bench.py --config $c --steps 10 --warmup 3 --deterministic --no-e2e --no-cpu-baseline --no-gpu-baseline --no-parity 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('det cfg$c', d['ms_per_step'], d['fwd_ms'], d['bwd_ms'])"; done

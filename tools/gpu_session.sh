@@ -24,7 +24,7 @@ for n in ("n1","ref","cfg0","cfg2","cfg3","det"):
         d=json.loads(open("gpurun_out/${tag}_bench_%s.json"%n).read().strip().splitlines()[-1])
         r=d.get("roofline") or {}
         print(n, "%.4g RoIs/s"%d["value"], "%.4f ms"%d["ms_per_step"], "fwd %.4f bwd %.4f"%(d.get("fwd_ms",0),d.get("bwd_ms",0)),
-              "step frac %.3f"%((r.get("fwd_plus_bwd") or {}).get("frac",0)), "serial %.4f"%((r.get("serial_r01_sequence") or {}).get("ms_per_step",0)),
+              "step frac %.3f"%((r.get("fwd_plus_bwd") or {}).get("frac",0)), "python %.4f"%((r.get("launched_from_python") or {}).get("ms_per_step",0)),
               "e2e", (d.get("e2e") or {}).get("value"), "parity", (d.get("parity") or {}).get("ok"))
     except Exception as e:
         print(n, "FAILED", e)

@@ -12,9 +12,9 @@ import json
 try:
     d=json.loads(open("gpurun_out/${tag}_v${i}_cfg$c.json").read().strip().splitlines()[-1])
     r=d["roofline"]
-    print("cfg$c [$o] step %.4f ms (frac %.3f) | launched fwd %.4f bwd %.4f | serial %.4f (fwd %.4f bwd %.4f) | parity %s fwd %.2e bwd %.2e" % (
-        d["ms_per_step"], r["fwd_plus_bwd"]["frac"], d["fwd_ms"], d["bwd_ms"], r["serial_r01_sequence"]["ms_per_step"],
-        r["serial_r01_sequence"]["fwd_ms"], r["serial_r01_sequence"]["bwd_ms"], d["parity"]["ok"],
+    print("cfg$c [$o] step %.4f ms (frac %.3f) | launched fwd %.4f bwd %.4f | from python %.4f (fwd %.4f bwd %.4f) | parity %s fwd %.2e bwd %.2e" % (
+        d["ms_per_step"], r["fwd_plus_bwd"]["frac"], d["fwd_ms"], d["bwd_ms"], r["launched_from_python"]["ms_per_step"],
+        r["launched_from_python"]["fwd_ms"], r["launched_from_python"]["bwd_ms"], d["parity"]["ok"],
         d["parity"].get("forward",{}).get("max_norm",-1), d["parity"].get("backward",{}).get("max_norm",-1)))
 except Exception as e:
     print("cfg$c [$o] FAILED", e); print(open("gpurun_out/${tag}_v${i}_cfg$c.err").read()[-1500:])
