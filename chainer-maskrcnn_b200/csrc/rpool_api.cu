@@ -463,7 +463,6 @@ static int det_prepass(const rpool_problem *p, void *ws, const Options &o, cudaS
     threads = o.threads;
     fill_params(p, w, o, true, threads, k);
     k.reverse = 0;
-    CUDA_TRY(cudaMemsetAsync(w.det_err, 0, sizeof(int), st), "cudaMemsetAsync(det_err)");
     if (p->n_rois > 0) {
         ScanParams sp;
         memset(&sp, 0, sizeof(sp));
@@ -475,10 +474,19 @@ static int det_prepass(const rpool_problem *p, void *ws, const Options &o, cudaS
         for (int h = 0; h < p->n_heads; ++h)
             sp.shapes_ok = sp.shapes_ok && p->out_h[h] <= kPBwd && p->out_w[h] <= kPBwd;
         sp.rects = w.rects; sp.woff = w.woff; sp.total = w.det_total; sp.err = w.det_err;
-        rpool_det_scan_kernel<<<1, 1024, 0, st>>>(sp);
-        CUDA_TRY(cudaGetLastError(), "rpool_det_scan_kernel launch");
+        // (resets the error flag itself.)  Under opt.zero_fill_in_tail's contract -- the kernel queued
+        // before this call neither touches the gradients nor produces the upstream gradients -- the scan
+        // starts in that kernel's tail: it reads the plan's records only.
+        if (o.fill_in_tail) {
+            CUDA_TRY(launch_in_tail(rpool_det_scan_kernel, dim3(1), dim3(kScanThreads), 0, st, sp),
+                     "rpool_det_scan_kernel launch");
+        } else {
+            rpool_det_scan_kernel<<<1, kScanThreads, 0, st>>>(sp);
+            CUDA_TRY(cudaGetLastError(), "rpool_det_scan_kernel launch");
+        }
         g_launches++;
     } else {
+        CUDA_TRY(cudaMemsetAsync(w.det_err, 0, sizeof(int), st), "cudaMemsetAsync(det_err)");
         CUDA_TRY(cudaMemsetAsync(w.det_total, 0, sizeof(unsigned long long), st), "cudaMemsetAsync(det_total)");
     }
     return RPOOL_OK;
@@ -548,8 +556,9 @@ static int backward_det(const rpool_problem *p, void *ws, const Options &o, cuda
         k.det_scratch_floats = p->det_workspace_bytes / sizeof(float);
         rc = set_smem(rpool_backward_kernel, 1, smem);
         if (rc) return rc;
-        rpool_backward_kernel<<<p->n_rois, threads, smem, st>>>(k);
-        CUDA_TRY(cudaGetLastError(), "rpool_backward_kernel launch");
+        // in the scan kernel's tail (waits before it reads the offsets)
+        CUDA_TRY(launch_in_tail(rpool_backward_kernel, dim3(p->n_rois), dim3(threads), (size_t)smem, st, k),
+                 "rpool_backward_kernel launch");
         g_launches++;
     }
     GatherParams g;
@@ -579,9 +588,19 @@ static int backward_det(const rpool_problem *p, void *ws, const Options &o, cuda
         // no plan was made: every group is empty
         CUDA_TRY(cudaMemsetAsync(w.gstart, 0, kGstartInts * sizeof(int), st), "cudaMemsetAsync(gstart)");
     }
-    if (p->channels <= 256) rpool_det_gather_kernel<2><<<(unsigned)ctas, kGatherWarps * 32, 0, st>>>(g);
-    else rpool_det_gather_kernel<kGatherSlabs><<<(unsigned)ctas, kGatherWarps * 32, 0, st>>>(g);
-    CUDA_TRY(cudaGetLastError(), "rpool_det_gather_kernel launch");
+    // in the backward launch's tail when there is one: lists its windows, waits before it reads them
+    const dim3 ggrid((unsigned)ctas), gblock(kGatherWarps * 32);
+    if (p->n_rois > 0) {
+        if (p->channels <= 256)
+            CUDA_TRY(launch_in_tail(rpool_det_gather_kernel<2>, ggrid, gblock, 0, st, g), "rpool_det_gather_kernel launch");
+        else
+            CUDA_TRY(launch_in_tail(rpool_det_gather_kernel<kGatherSlabs>, ggrid, gblock, 0, st, g),
+                     "rpool_det_gather_kernel launch");
+    } else {
+        if (p->channels <= 256) rpool_det_gather_kernel<2><<<ggrid, gblock, 0, st>>>(g);
+        else rpool_det_gather_kernel<kGatherSlabs><<<ggrid, gblock, 0, st>>>(g);
+        CUDA_TRY(cudaGetLastError(), "rpool_det_gather_kernel launch");
+    }
     g_launches++;
     return RPOOL_OK;
 }

@@ -668,7 +668,7 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     // The launch for the next pooled size may use this one's tail.  It does not wait for anything
     // itself, so when THIS launch started early (in the zero fill's tail, wait_fill) a CTA gives
     // the signal only once it has seen the fill complete -- see bwd_release.
-    if (!P.wait_fill) allow_dependents_early();
+    if (!P.wait_fill && !P.det) allow_dependents_early();
     const int kCtlBytes = (rec_bytes(P.n_heads) + 127) & ~127;   // only this launch's head parts are loaded
     constexpr int kTTabBytes = (sizeof(TTab) + 127) & ~127;
     TTab *tt = reinterpret_cast<TTab *>(smem_raw + kCtlBytes);
@@ -692,6 +692,12 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     }
 
     load_record(P, ctl);
+    if (P.det) {
+        // launched in the scan kernel's tail: its offsets from here on.  The gather launch queued behind
+        // this one lists its windows (rectangles: the scan's output) as soon as every CTA has got here.
+        wait_for_predecessors();
+        allow_dependents_early();
+    }
     RoiCtx c;
     ctx_from_record(P, ctl, c);
     if (!c.valid) { bwd_release(P); return; }
@@ -1133,33 +1139,42 @@ struct ScanParams {
     int *err;
 };
 
-__global__ void __launch_bounds__(1024)
+constexpr int kScanThreads = 256;   // (a small CTA: it fits beside the pooling CTAs still draining when it
+constexpr int kScanPer = 4;         //  starts in the previous launch's tail); slots per thread and round
+
+__global__ void __launch_bounds__(kScanThreads)
 rpool_det_scan_kernel(const __grid_constant__ ScanParams p)
 {
-    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long wsum[kScanThreads / 32];
     __shared__ unsigned long long carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry = 0;
+    allow_dependents_early();     // the backward launch loads its records meanwhile and waits before it reads the offsets
+    if (tid == 0) { carry = 0; *p.err = 0; }
     __syncthreads();
-    for (int base = 0; base < p.R; base += 1024) {
-        const int slot = base + tid;
-        unsigned long long v = 0ull;
-        if (slot < p.R) {
-            const int4 a = __ldg(reinterpret_cast<const int4 *>(p.recs + (size_t)slot * p.rec_stride));
-            const int4 f = __ldg(reinterpret_cast<const int4 *>(p.recs + (size_t)slot * p.rec_stride) + 1);
-            // a = wmin[0] (y0), wmin[1] (x0), wmax[0] (y1), wmax[1] (x1);  f = r, lvl, b, flags
-            const bool valid = (f.w & kRecValid) != 0;
-            const bool ok = p.shapes_ok && (f.w & (kRecShape | kRecFits)) == (kRecShape | kRecFits) &&
-                            a.z - a.x < kExt;
-            if (valid && !ok) atomicExch(p.err, 1);   // this RoI needs the generic path: not orderable
-            int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
-            if (valid && ok && a.w >= a.y && a.z >= a.x) {
-                x0 = a.y; y0 = a.x; x1 = a.w; y1 = a.z;
-                v = (unsigned long long)(x1 - x0 + 1) * (y1 - y0 + 1) * p.C;
+    for (int base = 0; base < p.R; base += kScanThreads * kScanPer) {
+        unsigned long long v[kScanPer], mine = 0ull;
+#pragma unroll
+        for (int u = 0; u < kScanPer; ++u) {
+            const int slot = base + tid * kScanPer + u;
+            v[u] = 0ull;
+            if (slot < p.R) {
+                const int4 a = __ldg(reinterpret_cast<const int4 *>(p.recs + (size_t)slot * p.rec_stride));
+                const int4 f = __ldg(reinterpret_cast<const int4 *>(p.recs + (size_t)slot * p.rec_stride) + 1);
+                // a = wmin[0] (y0), wmin[1] (x0), wmax[0] (y1), wmax[1] (x1);  f = r, lvl, b, flags
+                const bool valid = (f.w & kRecValid) != 0;
+                const bool ok = p.shapes_ok && (f.w & (kRecShape | kRecFits)) == (kRecShape | kRecFits) &&
+                                a.z - a.x < kExt;
+                if (valid && !ok) atomicExch(p.err, 1);   // this RoI needs the generic path: not orderable
+                int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
+                if (valid && ok && a.w >= a.y && a.z >= a.x) {
+                    x0 = a.y; y0 = a.x; x1 = a.w; y1 = a.z;
+                    v[u] = (unsigned long long)(x1 - x0 + 1) * (y1 - y0 + 1) * p.C;
+                }
+                *reinterpret_cast<int4 *>(p.rects + 4 * (size_t)slot) = make_int4(x0, y0, x1, y1);
             }
-            *reinterpret_cast<int4 *>(p.rects + 4 * (size_t)slot) = make_int4(x0, y0, x1, y1);
+            mine += v[u];
         }
-        unsigned long long x = v;
+        unsigned long long x = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
@@ -1167,23 +1182,22 @@ rpool_det_scan_kernel(const __grid_constant__ ScanParams p)
         }
         if (lane == 31) wsum[warp] = x;
         __syncthreads();
-        if (warp == 0) {
-            unsigned long long s = wsum[lane];
+        unsigned long long before = carry + x - mine;
+        for (int w = 0; w < warp; ++w) before += wsum[w];
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long y = __shfl_up_sync(0xffffffffu, s, d);
-                if (lane >= d) s += y;
-            }
-            wsum[lane] = s;
+        for (int u = 0; u < kScanPer; ++u) {
+            const int slot = base + tid * kScanPer + u;
+            if (slot < p.R) p.woff[slot] = before;
+            before += v[u];
         }
         __syncthreads();
-        const unsigned long long before = carry + (warp ? wsum[warp - 1] : 0ull) + x - v;
-        if (slot < p.R) p.woff[slot] = before;
-        __syncthreads();
-        if (tid == 0) carry += wsum[31];
+        if (tid == kScanThreads - 1) carry = before;
         __syncthreads();
     }
     if (tid == 0) *p.total = carry;
+    // (launched in the previous kernel's tail: this grid must not complete before that kernel has,
+    // because the launch behind it waits for THIS grid only)
+    wait_for_predecessors();
 }
 
 struct GatherParams {
@@ -1262,6 +1276,9 @@ rpool_det_gather_kernel(const __grid_constant__ GatherParams p)
             __syncthreads();
         }
         more = next < g1;
+        // (launched in the backward launch's tail: the private windows -- and the gradient map, when
+        // it is accumulated into -- from here on)
+        if (pass == 0) wait_for_predecessors();
         // ---- the strip's cells
         for (int x = xs + warp; x <= xe; x += kGatherWarps) {
             float *dst = L.data + (((size_t)b * L.H + y) * L.W + x) * C + lane * 4;
