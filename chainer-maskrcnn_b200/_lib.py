@@ -48,7 +48,7 @@ class Options(ctypes.Structure):
                 ("prefetch_rows", ctypes.c_int32),
                 ("prefetch_rois", ctypes.c_int32),
                 ("zero_fill_in_tail", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("backward_variant", ctypes.c_int32)]
 
 
 OPTION_NAMES = tuple(n for n, _ in Options._fields_ if n != "reserved")

@@ -25,7 +25,7 @@ constexpr int kMaxSmem = 227 * 1024;
 
 // rpool_options with the defaults filled in (0 = default in the ABI)
 struct Options {
-    int threads, order, force_path, split_heads, prefetch, fill_in_tail;
+    int threads, order, force_path, split_heads, prefetch, fill_in_tail, bwd_variant;
 };
 // CTA size of the pooling kernels when opt.cta_threads is 0: 4 warps per RoI, 4 such CTAs resident
 // per SM (register-limited).  A problem that does not even fill one wave of those (148 SMs x 4) is
@@ -152,8 +152,9 @@ int read_options(const rpool_problem *p, Options &o)
         return fail(RPOOL_ERR_INVALID, "opt.prefetch_rois=%d outside [0,65536]", q.prefetch_rois);
     if (q.zero_fill_in_tail < 0 || q.zero_fill_in_tail > 1)
         return fail(RPOOL_ERR_INVALID, "opt.zero_fill_in_tail=%d outside [0,1]", q.zero_fill_in_tail);
-    if (q.reserved)
-        return fail(RPOOL_ERR_INVALID, "opt.reserved must be zero");
+    if (q.backward_variant < 0 || q.backward_variant > 2)
+        return fail(RPOOL_ERR_INVALID, "opt.backward_variant=%d outside [0,2]", q.backward_variant);
+    o.bwd_variant = q.backward_variant;
     o.threads = q.cta_threads ? q.cta_threads
                               : (p->n_rois <= kOneWaveRois ? kSmallProblemThreads : kDefaultThreads);
     o.order = q.schedule;
@@ -270,11 +271,42 @@ int fill_params(const rpool_problem *p, const Workspace &w, const Options &o, bo
     return ctl + p->n_heads * ttab + warps * k.strip_cols * 512;
 }
 
+// SMs of the current device (cached per device).
+int sm_count()
+{
+    static std::atomic<int> cache[64];
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    const bool cached = dev >= 0 && dev < 64;
+    if (cached && cache[dev].load(std::memory_order_relaxed) > 0) return cache[dev].load(std::memory_order_relaxed);
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cached) cache[dev].store(n, std::memory_order_relaxed);
+    return n;
+}
+
+// The staged backward kernel serves this (one-pooled-size) problem: returns its grid size, 0 otherwise.
+int staged_grid(const rpool_problem *q, const Options &o, int &smem)
+{
+    if (o.bwd_variant != 2 || q->n_heads != 1 || q->deterministic || o.force_path == kPathGeneric) return 0;
+    if (q->feat_layout != RPOOL_NHWC || q->pool_layout != RPOOL_NHWC) return 0;
+    if (q->channels % 128 || q->channels > 128 * kStMaxSlabs) return 0;
+    if (q->out_h[0] > kPBwd || q->out_w[0] > kPBwd) return 0;
+    if (reinterpret_cast<uintptr_t>(q->pooled[0]) & 15) return 0;
+    smem = kStCtlBytes + 2 * kStRecBytes + 2 * q->out_h[0] * q->out_w[0] * 512;
+    if (smem > kMaxSmem) return 0;
+    const int sms = sm_count();
+    if (sms <= 0) return 0;
+    const int grid = q->n_rois < sms ? q->n_rois : sms;
+    if ((q->n_rois + grid - 1) / grid > kStMaxSlots) return 0;
+    return grid;
+}
+
 // Raises a pooling kernel's dynamic shared memory limit.  The limit is per device
 // and only ever needs to grow, so the largest value set so far is remembered per
 // (kernel, device) and the driver call is skipped when it already covers `smem`.
 constexpr int kSmemCacheDevices = 64;
-std::atomic<int> g_smem_set[2][kSmemCacheDevices];
+std::atomic<int> g_smem_set[3][kSmemCacheDevices];
 
 template <typename Kern>
 int set_smem(Kern kern, int which, int smem)
@@ -701,6 +733,22 @@ int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *strea
         // fill's tail: it waits before its first reduction (what it reads earlier -- the plan, gy --
         // was complete before the fill started, or is covered by opt.zero_fill_in_tail's contract)
         k.wait_fill = (part == 0 && !p->accumulate) ? 1 : 0;
+        int st_smem = 0;
+        const int st_grid = staged_grid(&q, o, st_smem);
+        if (st_grid > 0) {
+            k.staged_slots = (p->n_rois + st_grid - 1) / st_grid;
+            rc = set_smem(rpool_backward_staged_kernel, 2, st_smem);
+            if (rc) return rc;
+            if (part > 0 || !p->accumulate) {
+                CUDA_TRY(launch_in_tail(rpool_backward_staged_kernel, dim3(st_grid), dim3(kStThreads), (size_t)st_smem, st, k),
+                         "rpool_backward_staged_kernel launch");
+            } else {
+                rpool_backward_staged_kernel<<<st_grid, kStThreads, st_smem, st>>>(k);
+                CUDA_TRY(cudaGetLastError(), "rpool_backward_staged_kernel launch");
+            }
+            g_launches++;
+            continue;
+        }
         if (part > 0 || !p->accumulate) {
             CUDA_TRY(launch_in_tail(rpool_backward_kernel, dim3(p->n_rois), dim3(threads), (size_t)smem, st, k),
                      "rpool_backward_kernel launch");

@@ -66,6 +66,7 @@ struct KParams {
     int rec_head;    // first head part of the stored record this launch uses (0 unless heads are split)
     int force_path;
     int wait_fill;   // backward: this launch started in the zero fill's tail and must wait before it adds
+    int staged_slots; // staged backward: schedule slots per CTA (ceil(R / gridDim.x))
 };
 
 // ---------------------------------------------------------------------------
@@ -353,6 +354,40 @@ __device__ __forceinline__ void wait_for_predecessors()
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
+
+
+// ---------------------------------------------------------------------------
+// bulk copies (TMA unit) into shared memory, completion on an mbarrier
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+// makes the initialised barriers visible to the async proxy (the copy engine)
+__device__ __forceinline__ void mbar_init_fence()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// global -> this CTA's shared memory; bytes: multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
 }  // namespace rpool

@@ -184,10 +184,10 @@ __device__ __noinline__ void generic_forward(const KParams &P)
     }
 }
 
-__device__ __noinline__ void generic_backward(const KParams &P)
+__device__ __noinline__ void generic_backward(const KParams &P, int slot)
 {
     RoiCtx c;
-    roi_prologue(P, c);
+    roi_decode(P, slot, c);
     if (!c.valid) return;
     if (P.wait_fill) wait_for_predecessors();      // (see bwd_tasks: the gradients must be clean)
     const int C = P.C;
@@ -708,7 +708,7 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     const int y0 = ctl->wmin[0], y1 = ctl->wmax[0];
     if (!table_ok || y1 - y0 >= kExt) {
         if (P.det) { if (threadIdx.x == 0) atomicExch(P.det_err, 1); }   // no ordered generic path
-        else generic_backward(P);
+        else generic_backward(P, launch_slot(P));
         bwd_release(P);
         return;
     }
@@ -756,6 +756,296 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     for (int h = 0; h < P.n_heads; ++h) exact = exact && (P.PW[h] % kZ == 0);
     if (exact) bwd_tasks<256, true>(P, c, ctl, tt, strip, det_win);
     else bwd_tasks<0, false>(P, c, ctl, tt, strip, det_win);
+    bwd_release(P);
+}
+
+// ---------------------------------------------------------------------------
+// table path, backward, staged variant (atomic path, one pooled size per launch)
+// ---------------------------------------------------------------------------
+// Opt-in (opt.backward_variant = 2); measured slower than the rows kernel, kept as the reference point for
+// a copy-engine design of this pass (profiles/r02_experiments.log, r02w_staged_ncu_summary.txt).
+// One persistent CTA per SM.  The upstream gradient of a (RoI, 128-channel slab) item --
+// PH x PW pieces of 512 bytes, or PH contiguous bin rows when C = 128 -- is copied into shared
+// memory by the TMA unit (bulk copies completing on an mbarrier), two items deep, together with
+// the RoI's record; every byte of gy crosses L2 -> SM once (the rows kernel re-reads each bin row
+// for the 2-3 window rows it covers) and no load occupies a register while it is in flight.  The
+// CTA's warps take (item, window row) tasks from a shared counter, in order; a task sums its
+// covering bin rows straight from the staged item while it walks the bins (no strip), accumulates
+// the window cells of a chunk in registers as the rows kernel does and reduces them into the
+// gradient.  The warp that finishes the last task of an item refills its buffer with the item two
+// further on.
+// What the measurements say (B200): 512-byte bulk copies are bound by the copy engine's request
+// rate (~8 bytes per clock and SM: 0.42 ms for configs[1] against 0.19 ms); with one 7 KB copy per
+// bin row (C = 128) the staging keeps up, and the 8 warps that fit beside two staged items become
+// the limit -- issue slots 40 % busy at 2 warps per scheduler, no memory stall left (0.160 ms
+// against 0.125 ms); 16 warps leave no buffer loading in the background (0.177 ms).  One RoI's gy
+// (196 KB at C = 256) is the whole shared memory: data in flight plus the rows live under 16
+// concurrent tasks do not fit.
+constexpr int kStWarps = 8;
+constexpr int kStThreads = kStWarps * 32;
+constexpr int kStMaxSlots = 128;                  // schedule slots one CTA may own
+constexpr int kStMaxSlabs = 4;                    // C <= 512
+constexpr int kStMaxItems = kStMaxSlots * kStMaxSlabs;
+constexpr int kStCtlBytes = 6144;                 // control block
+constexpr int kStRecBytes = 2048;                 // one record (header + one head part), padded
+
+struct StagedCtl {
+    unsigned long long full[2];        // mbarriers: item data + record have landed in buffer b
+    int loaded[2];                     // item whose copies were issued into buffer b
+    int done[2];                       // finished tasks of the item in buffer b
+    int next_task, n_items, total_tasks, pad_;
+    int pref[kStMaxItems + 1];         // first task of every item
+    unsigned short item[kStMaxItems];  // owned slot index * 4 + slab
+    int r[kStMaxSlots];                // RoI of every owned slot
+    short hc[kStMaxSlots];             // window rows of every owned slot (0: nothing to do here)
+    unsigned char gen[kStMaxSlots];    // the slot needs the generic path
+};
+static_assert(sizeof(StagedCtl) <= kStCtlBytes, "staged control block");
+static_assert(kRecHeader + sizeof(HeadCtl) <= kStRecBytes, "staged record slot");
+
+template <int NX, int R>
+__device__ __forceinline__ void st_bins_at(float4 (&G)[kSW], unsigned long long cnt, const float4 *&wp,
+                                           uint32_t &zp, uint32_t o1, uint32_t rs, int nr,
+                                           float w0, float w1, float w2, float w3)
+{
+    const int n = (int)((cnt >> (8 * R)) & 0xffull);
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        const float4 w = *wp;
+        const float4 a0 = lds128(zp);
+        const float4 a1 = lds128(zp + o1);       // (a single covering row: row 0 again, weight 0)
+        float4 z = mul4(w0, a0);
+        fma4(z, w1, a1);
+        if (nr > 2) fma4(z, w2, lds128(zp + 2 * rs));
+        if (nr > 3) fma4(z, w3, lds128(zp + 3 * rs));
+        fma4(G[R], w.x, z);
+        if (NX > 1 && R + 1 < kSW) fma4(G[R + 1], w.y, z);
+        if (NX > 2 && R + 2 < kSW) fma4(G[R + 2], w.z, z);
+        if (NX > 3 && R + 3 < kSW) fma4(G[R + 3], w.w, z);
+        ++wp;
+        zp += 512u;
+    }
+}
+
+template <int NX>
+__device__ __forceinline__ void st_col_pass(float4 (&G)[kSW], unsigned long long cnt, const float4 *wp,
+                                            uint32_t zp, uint32_t o1, uint32_t rs, int nr,
+                                            float w0, float w1, float w2, float w3)
+{
+    st_bins_at<NX, 0>(G, cnt, wp, zp, o1, rs, nr, w0, w1, w2, w3);
+    st_bins_at<NX, 1>(G, cnt, wp, zp, o1, rs, nr, w0, w1, w2, w3);
+    st_bins_at<NX, 2>(G, cnt, wp, zp, o1, rs, nr, w0, w1, w2, w3);
+    st_bins_at<NX, 3>(G, cnt, wp, zp, o1, rs, nr, w0, w1, w2, w3);
+    st_bins_at<NX, 4>(G, cnt, wp, zp, o1, rs, nr, w0, w1, w2, w3);
+    st_bins_at<NX, 5>(G, cnt, wp, zp, o1, rs, nr, w0, w1, w2, w3);
+    st_bins_at<NX, 6>(G, cnt, wp, zp, o1, rs, nr, w0, w1, w2, w3);
+    st_bins_at<NX, 7>(G, cnt, wp, zp, o1, rs, nr, w0, w1, w2, w3);
+}
+
+// One task: window row i of the item staged at `buf` (record `ctl`), channels slab * 128 + lane * 4.
+template <int kC>
+__device__ __forceinline__ void staged_task(const KParams &P, const BlockCtl *ctl, uint32_t buf, int i, int slab,
+                                            int lane, bool &waited)
+{
+    const int C = kC ? kC : P.C;
+    const int PH = P.PH[0], PW = P.PW[0];
+    const HeadCtl &hd = ctl->hd[0];
+    const AxisTab &yt = hd.tab[0];
+    const AxisTab &xt = hd.tab[1];
+    const int y = ctl->wmin[0] + i;
+    // the bin rows whose footprint holds window row y: an interval (footprints start at non-decreasing rows)
+    const bool cov = lane < PH && yt.lo[lane] <= y && y < yt.lo[lane] + yt.n[lane];
+    const unsigned m = __ballot_sync(0xffffffffu, cov);
+    if (!m) return;
+    const int pa = __ffs(m) - 1, pb = 32 - __clz(m);
+    const LevelDev L = P.lvl[ctl->lvl];
+    float *grow = L.data + (((size_t)ctl->b * L.H + y) * L.W) * C + slab * 128 + lane * 4;
+    const uint32_t rs = (uint32_t)PW * 512u;
+    const int NX = hd.nmax[1];
+    const int nchunk = hd.nchunk;
+    for (int q = 0; q < nchunk; ++q) {
+        const int pa_q = hd.cstart[q];
+        const unsigned long long cnt = hd.ccnt[q];
+        float4 G[kSW];
+#pragma unroll
+        for (int s = 0; s < kSW; ++s) G[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g = pa; g < pb; g += 4) {       // (more than four covering rows: tiny RoIs)
+            const int nr = pb - g < 4 ? pb - g : 4;
+            const float w0 = wy_of(yt, g, y);
+            const float w1 = nr > 1 ? wy_of(yt, g + 1, y) : 0.f;
+            const float w2 = nr > 2 ? wy_of(yt, g + 2, y) : 0.f;
+            const float w3 = nr > 3 ? wy_of(yt, g + 3, y) : 0.f;
+            const uint32_t zp = buf + (uint32_t)(g * PW + pa_q) * 512u + (uint32_t)lane * 16u;
+            const float4 *wp = &xt.w[pa_q];
+            const uint32_t o1 = nr > 1 ? rs : 0u;
+            if (NX <= 2) st_col_pass<2>(G, cnt, wp, zp, o1, rs, nr, w0, w1, w2, w3);
+            else if (NX == 3) st_col_pass<3>(G, cnt, wp, zp, o1, rs, nr, w0, w1, w2, w3);
+            else st_col_pass<4>(G, cnt, wp, zp, o1, rs, nr, w0, w1, w2, w3);
+        }
+        // (launched in the zero fill's tail: the gradients must be clean before the first reduction)
+        if (P.wait_fill && !waited) { wait_for_predecessors(); waited = true; }
+        const unsigned cm = hd.cmask[q];
+        float *gp = grow + (size_t)hd.cx0[q] * C;
+#pragma unroll
+        for (int s = 0; s < kSW; ++s)
+            if ((cm >> s) & 1u) red_add_v4(gp + (kC ? s * kC : s * C), G[s]);
+    }
+}
+
+__device__ __forceinline__ int staged_slot(const KParams &P, int k)
+{
+    const int idx = (int)blockIdx.x + k * (int)gridDim.x;      // launch order
+    return P.reverse ? P.R - 1 - idx : idx;
+}
+
+// Issues the copies of item j into buffer b (one warp, converged).
+__device__ __forceinline__ void staged_issue(const KParams &P, StagedCtl *sc, uint32_t smem_base, int item_bytes,
+                                             int j, int b, int lane)
+{
+    const int code = sc->item[j];
+    const int k = code >> 2, slab = code & 3;
+    const int PHW = P.PH[0] * P.PW[0];
+    const uint32_t bar = smem_u32(&sc->full[b]);
+    const uint32_t rec_dst = smem_base + kStCtlBytes + (uint32_t)b * kStRecBytes;
+    const uint32_t buf = smem_base + kStCtlBytes + 2u * kStRecBytes + (uint32_t)b * (uint32_t)item_bytes;
+    const unsigned char *rec = P.recs + (size_t)staged_slot(P, k) * P.rec_stride;
+    // (the buffer's previous readers are done: ordered by the done counter; generic-proxy reads
+    // before async-proxy writes)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(kRecHeader + sizeof(HeadCtl)) + (uint32_t)PHW * 512u);
+    __syncwarp();
+    if (lane == 0) bulk_g2s(rec_dst, rec, kRecHeader, bar);
+    if (lane == 1) bulk_g2s(rec_dst + kRecHeader, rec + kRecHeader + (size_t)P.rec_head * sizeof(HeadCtl),
+                            (uint32_t)sizeof(HeadCtl), bar);
+    const float *src = P.pooled[0] + (size_t)sc->r[k] * PHW * P.C + slab * 128;
+    if (P.C == 128) {
+        // one slab wide: a bin row is contiguous
+        if (lane < P.PH[0])
+            bulk_g2s(buf + (uint32_t)(lane * P.PW[0]) * 512u, src + (size_t)lane * P.PW[0] * 128,
+                     (uint32_t)P.PW[0] * 512u, bar);
+    } else {
+        for (int pcs = lane; pcs < PHW; pcs += 32)
+            bulk_g2s(buf + (uint32_t)pcs * 512u, src + (size_t)pcs * P.C, 512u, bar);
+    }
+    // the upstream gradient of the RoI this CTA takes up two items further on: into L2 meanwhile
+    if (slab == 0 && k + 2 < P.staged_slots) {
+        const int slot2 = staged_slot(P, k + 2);
+        if (slot2 >= 0 && slot2 < P.R && sc->hc[k + 2] > 0 && lane < P.PH[0]) {
+            const size_t row_floats = (size_t)P.PW[0] * P.C;
+            prefetch_l2_bulk(P.pooled[0] + ((size_t)sc->r[k + 2] * P.PH[0] + lane) * row_floats,
+                             (unsigned)(row_floats * 4));
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        *reinterpret_cast<volatile int *>(&sc->loaded[b]) = j;
+    }
+}
+
+__global__ void __launch_bounds__(kStThreads, 1)
+rpool_backward_staged_kernel(const __grid_constant__ KParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StagedCtl *sc = reinterpret_cast<StagedCtl *>(smem_raw);
+    const uint32_t smem_base = smem_u32(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int PHW = P.PH[0] * P.PW[0];
+    const int item_bytes = PHW * 512;
+    const int slabs = P.C >> 7;
+    if (!P.wait_fill) allow_dependents_early();
+
+    // ---- this CTA's schedule slots: window rows, RoI index, which path
+    int n_my = 0;
+    for (int k = 0; k < P.staged_slots; ++k) {
+        const int idx = (int)blockIdx.x + k * (int)gridDim.x;
+        if (idx < P.R) n_my = k + 1;
+    }
+    for (int k = tid; k < n_my; k += kStThreads) {
+        const unsigned char *rec = P.recs + (size_t)staged_slot(P, k) * P.rec_stride;
+        const int4 a = __ldg(reinterpret_cast<const int4 *>(rec));        // wmin[0], wmin[1], wmax[0], wmax[1]
+        const int4 f = __ldg(reinterpret_cast<const int4 *>(rec) + 1);    // r, lvl, b, flags
+        const bool valid = (f.w & kRecValid) != 0;
+        const int need = kRecShape | kRecFits;
+        const bool table_ok = (f.w & need) == need && P.force_path != kPathGeneric &&
+                              pointers_aligned(P, P.lvl[f.y]);
+        int hc = 0;
+        if (valid && table_ok && a.w >= a.y && a.z >= a.x) hc = a.z - a.x + 1;
+        sc->hc[k] = (short)(hc > 32767 ? 32767 : hc);
+        sc->gen[k] = (valid && !table_ok) ? 1 : 0;
+        sc->r[k] = f.x;
+    }
+    if (tid == 0) {
+        mbar_init(smem_u32(&sc->full[0]), 1);
+        mbar_init(smem_u32(&sc->full[1]), 1);
+        mbar_init_fence();
+        sc->loaded[0] = sc->loaded[1] = -1;
+        sc->done[0] = sc->done[1] = 0;
+        sc->next_task = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int n = 0, pref = 0;
+        for (int k = 0; k < n_my; ++k) {
+            const int hc = sc->hc[k];
+            if (hc <= 0) continue;
+            for (int sl = 0; sl < slabs; ++sl) {
+                sc->item[n] = (unsigned short)(k * 4 + sl);
+                sc->pref[n] = pref;
+                pref += hc;
+                ++n;
+            }
+        }
+        sc->pref[n] = pref;
+        sc->n_items = n;
+        sc->total_tasks = pref;
+    }
+    __syncthreads();
+    // ---- RoIs outside the table path (rare): tap by tap, the whole CTA
+    for (int k = 0; k < n_my; ++k)
+        if (sc->gen[k]) generic_backward(P, staged_slot(P, k));
+    const int n_items = sc->n_items, total = sc->total_tasks;
+    if (warp == 0) {
+        if (n_items > 0) staged_issue(P, sc, smem_base, item_bytes, 0, 0, lane);
+        if (n_items > 1) staged_issue(P, sc, smem_base, item_bytes, 1, 1, lane);
+    }
+
+    // ---- tasks
+    int j = 0;
+    bool waited = false;
+    for (;;) {
+        int seq = 0;
+        if (lane == 0) seq = atomicAdd(&sc->next_task, 1);
+        seq = __shfl_sync(0xffffffffu, seq, 0);
+        if (seq >= total) break;
+        while (seq >= sc->pref[j + 1]) ++j;
+        const int i = seq - sc->pref[j];
+        const int b = j & 1;
+        if (lane == 0)
+            while (*reinterpret_cast<volatile int *>(&sc->loaded[b]) != j) __nanosleep(40);
+        __syncwarp();
+        const uint32_t bar = smem_u32(&sc->full[b]);
+        while (!mbar_try_wait(bar, (uint32_t)((j >> 1) & 1))) {}
+        const BlockCtl *ctl = reinterpret_cast<const BlockCtl *>(smem_raw + kStCtlBytes + b * kStRecBytes);
+        const uint32_t buf = smem_base + kStCtlBytes + 2u * kStRecBytes + (uint32_t)b * (uint32_t)item_bytes;
+        const int slab = sc->item[j] & 3;
+        if (P.C == 256) staged_task<256>(P, ctl, buf, i, slab, lane, waited);
+        else staged_task<0>(P, ctl, buf, i, slab, lane, waited);
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+            __threadfence_block();
+            const int d = atomicAdd(&sc->done[b], 1);
+            last = (d == sc->pref[j + 1] - sc->pref[j] - 1) ? 1 : 0;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            // every task of item j is finished: its buffer takes item j + 2
+            if (lane == 0) { sc->done[b] = 0; __threadfence_block(); }
+            __syncwarp();
+            if (j + 2 < n_items) staged_issue(P, sc, smem_base, item_bytes, j + 2, b, lane);
+        }
+    }
     bwd_release(P);
 }
 

@@ -112,7 +112,11 @@ typedef struct rpool_options {
                              * the gradient buffers nor produces the upstream gradients -- e.g. it is this
                              * problem's rpool_forward, as in the step helper of the Python package.
                              * 0 = plain stream order */
-    int32_t reserved;       /* must be zero */
+    int32_t backward_variant; /* rpool_backward, atomic path: 0 or 1 = "rows" kernel (a CTA per RoI, gy through
+                             * registers; the default), 2 = "staged" kernel (a persistent CTA per SM, gy copied
+                             * into shared memory by the TMA unit; measured slower) where it
+                             * applies -- channels-last, C a multiple of 128 up to 512, one pooled size per
+                             * launch whose staged item fits, at most 128 RoIs per SM -- and rows elsewhere */
 } rpool_options;
 
 /* One pyramid level.  `data` is the feature map in rpool_forward (read) and

@@ -58,6 +58,9 @@ CONFIGS = {
     # what ONE of 8 GPUs holds when configs[3] is sharded by image (tuning aid: same shapes, 2 images)
     13: dict(name="cfg3_one_eighth_2img_1000rois", n_images=2, height=800, width=1333,
              rois_per_image=1000, out_sizes=[7, 14], n_levels=4, channels=256, aspect=(0.5, 2.0)),
+    # configs[1] with half the channels (tuning aid: a bin row of gy is one slab wide)
+    21: dict(name="cfg1_mask14_128ch", n_images=2, height=800, width=1333,
+             rois_per_image=2048, out_sizes=[14], n_levels=4, channels=128, aspect=(0.5, 2.0)),
 }
 
 

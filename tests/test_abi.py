@@ -77,7 +77,8 @@ def test_options_validation():
     raw = ctypes.create_string_buffer(65536 + 16)
     ws = ctypes.c_void_p((ctypes.addressof(raw) + 15) & ~15)
     for bad in (dict(cta_threads=100), dict(cta_threads=512), dict(schedule=4), dict(force_path=3),
-                dict(prefetch_rows=17), dict(prefetch_rois=-1), dict(fuse_heads_backward=2)):
+                dict(prefetch_rows=17), dict(prefetch_rois=-1), dict(fuse_heads_backward=2),
+                dict(backward_variant=3)):
         p = _problem()
         p.opt = _lib.make_options(**bad)
         for fn in (L.rpool_plan, L.rpool_forward, L.rpool_backward):

@@ -208,6 +208,40 @@ def test_block_sizes(threads):
         assert oracle.rel_err(g, w) <= BWD_TOL
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("mode_name,S,sizes,C,size", [
+    ("caffe2", 2, [14], 256, (8.0, 300.0)), ("chainer", 1, [14], 256, (8.0, 300.0)),
+    ("caffe2", 2, [7, 14], 128, (8.0, 300.0)), ("caffe2", 0, [7], 384, (8.0, 300.0)),
+    ("caffe2", 2, [14], 256, (1.0, 12.0)),      # tiny RoIs: many bin rows on one window row
+    ("caffe2", 1, [16], 128, (8.0, 300.0)), ("caffe2", 2, [14], 64, (8.0, 300.0))])   # (C = 64: rows kernel either way)
+def test_backward_variants(variant, mode_name, S, sizes, C, size):
+    """opt.backward_variant: the rows kernel (a CTA per RoI) and the staged kernel (persistent CTAs,
+    gy through shared memory by bulk copies) both match the oracle."""
+    rng, feats, rois, levels, scales = make_case(seed=51 + S, C=C, per_img=400, size=size)
+    mode = _lib.COORD_CHAINER if mode_name == "chainer" else _lib.COORD_CAFFE2
+    gys = [synth.make_gy(rng, rois.shape[0], C, P) for P in sizes]
+    _, grads, _ = run_fused(feats, rois, levels, scales, sizes, S, mode, gys=gys,
+                            options=dict(backward_variant=variant))
+    _, want = oracle_fused(feats, rois, levels, scales, sizes, S, mode_name, gys)
+    for g, w in zip(grads, want):
+        assert oracle.rel_err(g, w) <= BWD_TOL
+
+
+def test_staged_backward_few_rois_and_bad_rois():
+    """Fewer RoIs than SMs, a RoI of an image outside the batch, one RoI only."""
+    rng, feats, rois, levels, scales = make_case(seed=61, C=128, per_img=20)
+    for n in (1, 7, 40):
+        r2 = rois[:n].copy()
+        if n > 3:
+            r2[3, 0] = 9
+        lv = levels[:n]
+        gy = synth.make_gy(rng, n, 128, 14)
+        _, a, _ = run_fused(feats, r2, lv, scales, [14], 2, gys=[gy], options=dict(backward_variant=2))
+        _, b, _ = run_fused(feats, r2, lv, scales, [14], 2, gys=[gy], options=dict(backward_variant=1))
+        for x, y in zip(a, b):
+            assert oracle.rel_err(x, y) <= BWD_TOL
+
+
 @pytest.mark.parametrize("split", [0, 1])
 @pytest.mark.parametrize("mode_name,S", [("chainer", 1), ("caffe2", 2)])
 def test_two_pooled_sizes_backward_fused_or_one_launch_per_size(split, mode_name, S):
