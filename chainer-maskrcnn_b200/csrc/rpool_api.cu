@@ -616,6 +616,7 @@ static int backward_det(const rpool_problem *p, void *ws, const Options &o, cuda
     g.accumulate = p->accumulate;
     g.gstart = w.gstart; g.rects = w.rects; g.woff = w.woff;
     g.scratch = static_cast<const float *>(p->det_workspace);
+    g.scratch_floats = p->det_workspace_bytes / sizeof(float);
     if (p->n_rois == 0) {
         // no plan was made: every group is empty
         CUDA_TRY(cudaMemsetAsync(w.gstart, 0, kGstartInts * sizeof(int), st), "cudaMemsetAsync(gstart)");

@@ -1500,11 +1500,17 @@ struct GatherParams {
     const int *rects;                      // per slot: x0, y0, x1, y1 of the RoI's window
     const unsigned long long *woff;        // per slot: float offset of its private window
     const float *scratch;
+    unsigned long long scratch_floats;     // windows that end beyond it were never written (flagged by the
+                                           // window pass): they are not listed, so nothing outside is read
 };
 
 constexpr int kGatherWarps = 8;       // cells in flight per CTA
 constexpr int kGatherList = 1024;     // windows a CTA lists per pass
 constexpr int kGatherSlabs = 4;       // 128-channel slabs held in registers: C <= 512
+#ifndef RPOOL_EXP_GATHER_U
+#define RPOOL_EXP_GATHER_U 4
+#endif
+constexpr int kGatherU = RPOOL_EXP_GATHER_U;   // windows whose loads are in flight together (per warp)
 
 // One CTA per strip of a map row (a few CTAs per row: wide strips on the fine levels, where most
 // cells are covered by nothing and the CTA's fixed cost would otherwise dominate).  The CTA lists,
@@ -1548,6 +1554,11 @@ rpool_det_gather_kernel(const __grid_constant__ GatherParams p)
                 rc = __ldg(reinterpret_cast<const int4 *>(p.rects) + slot);
                 hit = rc.y <= y && y <= rc.w && rc.x <= xe && rc.z >= xs;
             }
+            unsigned long long woff = 0ull;
+            if (hit) {
+                woff = __ldg(p.woff + slot);
+                hit = woff + (unsigned long long)(rc.z - rc.x + 1) * (rc.w - rc.y + 1) * C <= p.scratch_floats;
+            }
             const unsigned m = __ballot_sync(0xffffffffu, hit);
             if (lane == 0) s_wcount[warp] = __popc(m);
             __syncthreads();
@@ -1559,7 +1570,7 @@ rpool_det_gather_kernel(const __grid_constant__ GatherParams p)
             }
             if (hit) {
                 s_x0[pos] = rc.x; s_x1[pos] = rc.z; s_y0[pos] = rc.y; s_wc[pos] = rc.z - rc.x + 1;
-                s_off[pos] = __ldg(p.woff + slot);
+                s_off[pos] = woff;
             }
             n += total;
             next += kGatherWarps * 32;
@@ -1589,9 +1600,9 @@ rpool_det_gather_kernel(const __grid_constant__ GatherParams p)
                 if (cov) mine = s_off[e] + ((unsigned long long)(y - s_y0[e]) * s_wc[e] + (x - s_x0[e])) * C;
                 unsigned hits = __ballot_sync(0xffffffffu, cov);
                 while (hits) {
-                    float4 v[4][kSlabs];
+                    float4 v[kGatherU][kSlabs];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < kGatherU; ++u) {
                         const int src_lane = hits ? __ffs(hits) - 1 : 0;
                         const bool on = hits != 0;
                         hits &= hits - 1;
@@ -1604,7 +1615,7 @@ rpool_det_gather_kernel(const __grid_constant__ GatherParams p)
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
+                    for (int u = 0; u < kGatherU; ++u)
 #pragma unroll
                         for (int k = 0; k < kSlabs; ++k) {
                             acc[k].x += v[u][k].x; acc[k].y += v[u][k].y; acc[k].z += v[u][k].z; acc[k].w += v[u][k].w;
@@ -1615,7 +1626,7 @@ rpool_det_gather_kernel(const __grid_constant__ GatherParams p)
             for (int k = 0; k < kSlabs; ++k)
                 if (k * 128 + lane * 4 < C) stg128(dst + k * 128, acc[k]);
         }
-        __syncthreads();       // the list is consumed before the next pass overwrites it
+        if (more) __syncthreads();       // the list is consumed before the next pass overwrites it
     }
 }
 
