@@ -604,7 +604,7 @@ static int backward_det(const rpool_problem *p, void *ws, const Options &o, cuda
         g.lvl[l].W = p->level[l].width;
         // at most 8 CTAs per map row: strips of 8, 16, 24 ... cells
         const int groups = (p->level[l].width + kGatherWarps - 1) / kGatherWarps;
-        g.cells[l] = kGatherWarps * ((groups + 7) / 8);
+        g.cells[l] = kGatherWarps * ((groups + kGatherRowCtas - 1) / kGatherRowCtas);
         g.strips[l] = (p->level[l].width + g.cells[l] - 1) / g.cells[l];
         g.strip_base[li] = ctas;
         ctas += (long long)p->level[l].n_images * p->level[l].height * g.strips[l];

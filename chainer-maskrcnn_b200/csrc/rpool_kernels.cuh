@@ -1505,12 +1505,11 @@ struct GatherParams {
 };
 
 constexpr int kGatherWarps = 8;       // cells in flight per CTA
+constexpr int kGatherRowCtas = 8;     // at most this many CTAs per map row
 constexpr int kGatherList = 1024;     // windows a CTA lists per pass
 constexpr int kGatherSlabs = 4;       // 128-channel slabs held in registers: C <= 512
-#ifndef RPOOL_EXP_GATHER_U
-#define RPOOL_EXP_GATHER_U 4
-#endif
-constexpr int kGatherU = RPOOL_EXP_GATHER_U;   // windows whose loads are in flight together (per warp)
+constexpr int kGatherU = 4;           // windows whose loads are in flight together (per warp); 6 or 8 cost
+                                      // more in resident warps than they gain (profiles/r02_experiments.log)
 
 // One CTA per strip of a map row (a few CTAs per row: wide strips on the fine levels, where most
 // cells are covered by nothing and the CTA's fixed cost would otherwise dominate).  The CTA lists,
@@ -1626,7 +1625,9 @@ rpool_det_gather_kernel(const __grid_constant__ GatherParams p)
             for (int k = 0; k < kSlabs; ++k)
                 if (k * 128 + lane * 4 < C) stg128(dst + k * 128, acc[k]);
         }
-        if (more) __syncthreads();       // the list is consumed before the next pass overwrites it
+        // the list is consumed before the next pass overwrites it.  (No barrier after the last pass: a warp
+        // that has finished its cells leaves at once -- with the barrier the gather ran 159 us instead of 120.)
+        if (more) __syncthreads();
     }
 }
 
