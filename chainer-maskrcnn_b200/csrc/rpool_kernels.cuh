@@ -21,6 +21,10 @@
 
 namespace rpool {
 
+#ifndef RPOOL_EXP_REC_AHEAD
+#define RPOOL_EXP_REC_AHEAD 0
+#endif
+
 // ---------------------------------------------------------------------------
 // shared prologue: RoI decode + tables
 // ---------------------------------------------------------------------------
@@ -88,6 +92,15 @@ __device__ __forceinline__ void load_record(const KParams &P, BlockCtl *ctl)
     const int n16 = rec_bytes(P.n_heads) >> 4;
     for (int i = threadIdx.x; i < n16; i += blockDim.x)
         dst[i] = __ldg(src + (i < kHdr16 ? i : i + skip16));
+#if RPOOL_EXP_REC_AHEAD > 0
+    // the record of the CTA scheduled kRecAhead places later: into L2 meanwhile (by the time that CTA
+    // starts, the pooled maps streaming through L2 would have pushed the plan's output out to HBM)
+    if (threadIdx.x == 32 && (int)blockIdx.x + RPOOL_EXP_REC_AHEAD < P.R) {
+        const int ahead = (int)blockIdx.x + RPOOL_EXP_REC_AHEAD;
+        const int slot = P.reverse ? P.R - 1 - ahead : ahead;
+        prefetch_l2_bulk(P.recs + (size_t)slot * P.rec_stride, (unsigned)P.rec_stride);
+    }
+#endif
     __syncthreads();
 }
 
