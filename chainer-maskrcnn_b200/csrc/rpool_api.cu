@@ -265,6 +265,8 @@ int fill_params(const rpool_problem *p, const Workspace &w, const Options &o, bo
     k.det_err = w.det_err;
     k.recs = bwd ? w.recs_bwd : w.recs_fwd;
     k.rec_stride = w.rec_stride;
+    k.tail_start = p->n_rois;
+    k.tail_parts = 1;
     if (!bwd) return ctl;
     const int ttab = (int)((sizeof(TTab) + 127) & ~(size_t)127);
     k.strip_cols = sum_pw > 0 ? sum_pw : 1;
@@ -322,6 +324,32 @@ int set_smem(Kern kern, int which, int smem)
         while (seen < smem && !g_smem_set[which][dev].compare_exchange_weak(seen, smem)) {}
     }
     return RPOOL_OK;
+}
+
+// Split tail of a pooling launch (KParams::tail_start / tail_parts): the last resident-CTAs' worth of
+// work is handed out in `parts` pieces per RoI, so that the launch drains in 1 / parts of a full CTA's
+// duration.  Only for launches of more than two waves; returns the grid size.
+// Measured (profiles/r02_experiments.log, r03j..l): two pieces per RoI in the forward launch's tail take
+// 2.4 % off the forward of configs[1] and 5.3 % off a 2 000-RoI shard of configs[3]; three or four pieces
+// are no better; the backward launch, which already ends on its shortest CTAs, does not gain.
+constexpr int kTailPartsFwd = 2, kTailPartsBwd = 1;
+template <typename Kern>
+int split_tail(Kern kern, int threads, int smem, int parts, KParams &k)
+{
+    k.tail_start = k.R;
+    k.tail_parts = 1;
+    if (parts < 2 || k.det || k.prefetch >= 0) return k.R;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return k.R;
+    }
+    const int resident = per_sm * sm_count();
+    if (resident <= 0 || k.R < 2 * resident) return k.R;
+    const int split = resident / parts;            // RoIs served in pieces
+    k.tail_start = k.R - split;
+    k.tail_parts = parts;
+    return k.tail_start + split * parts;
 }
 
 }  // namespace
@@ -469,7 +497,8 @@ int rpool_forward(const rpool_problem *p, void *ws, size_t ws_size, void *stream
     if (rc) return rc;
     // (always safe: the kernel's first instruction waits for everything queued before it; what the
     // early start buys is the launch ramp, hidden in the plan kernel's tail)
-    CUDA_TRY(launch_in_tail(rpool_forward_kernel, dim3(p->n_rois), dim3(threads), (size_t)smem,
+    const int grid = split_tail(rpool_forward_kernel, threads, smem, kTailPartsFwd, k);
+    CUDA_TRY(launch_in_tail(rpool_forward_kernel, dim3(grid), dim3(threads), (size_t)smem,
                             static_cast<cudaStream_t>(stream), k), "rpool_forward_kernel launch");
     g_launches++;
     return RPOOL_OK;
@@ -709,7 +738,18 @@ int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *strea
     // size keeps the per-CTA strips small (more L1 for the gy re-reads): 2 launches unless
     // opt.fuse_heads_backward is set.
     const int parts = (p->n_heads > 1 && o.split_heads) ? p->n_heads : 1;
-    for (int part = 0; part < parts; ++part) {
+    // (launch order: the pooled size with the most bins first -- its CTAs are the long ones; the launch
+    // that drains with nothing queued behind it is then the one with the short CTAs)
+    int head_order[RPOOL_MAX_HEADS];
+    for (int h = 0; h < RPOOL_MAX_HEADS; ++h) head_order[h] = h;
+    if (parts > 1)
+        for (int a = 0; a < parts; ++a)
+            for (int b = a + 1; b < parts; ++b)
+                if (p->out_h[head_order[b]] * p->out_w[head_order[b]] > p->out_h[head_order[a]] * p->out_w[head_order[a]]) {
+                    const int t = head_order[a]; head_order[a] = head_order[b]; head_order[b] = t;
+                }
+    for (int pi = 0; pi < parts; ++pi) {
+        const int part = parts > 1 ? head_order[pi] : 0;
         rpool_problem q = *p;
         if (parts > 1) {
             q.n_heads = 1;
@@ -733,14 +773,14 @@ int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *strea
         // ... and the first one, when this call's own zero fill is the kernel before it, may start in the
         // fill's tail: it waits before its first reduction (what it reads earlier -- the plan, gy --
         // was complete before the fill started, or is covered by opt.zero_fill_in_tail's contract)
-        k.wait_fill = (part == 0 && !p->accumulate) ? 1 : 0;
+        k.wait_fill = (pi == 0 && !p->accumulate) ? 1 : 0;
         int st_smem = 0;
         const int st_grid = staged_grid(&q, o, st_smem);
         if (st_grid > 0) {
             k.staged_slots = (p->n_rois + st_grid - 1) / st_grid;
             rc = set_smem(rpool_backward_staged_kernel, 2, st_smem);
             if (rc) return rc;
-            if (part > 0 || !p->accumulate) {
+            if (pi > 0 || !p->accumulate) {
                 CUDA_TRY(launch_in_tail(rpool_backward_staged_kernel, dim3(st_grid), dim3(kStThreads), (size_t)st_smem, st, k),
                          "rpool_backward_staged_kernel launch");
             } else {
@@ -750,11 +790,12 @@ int rpool_backward(const rpool_problem *p, void *ws, size_t ws_size, void *strea
             g_launches++;
             continue;
         }
-        if (part > 0 || !p->accumulate) {
-            CUDA_TRY(launch_in_tail(rpool_backward_kernel, dim3(p->n_rois), dim3(threads), (size_t)smem, st, k),
+        const int grid = split_tail(rpool_backward_kernel, threads, smem, kTailPartsBwd, k);
+        if (pi > 0 || !p->accumulate) {
+            CUDA_TRY(launch_in_tail(rpool_backward_kernel, dim3(grid), dim3(threads), (size_t)smem, st, k),
                      "rpool_backward_kernel launch");
         } else {
-            rpool_backward_kernel<<<p->n_rois, threads, smem, st>>>(k);
+            rpool_backward_kernel<<<grid, threads, smem, st>>>(k);
             CUDA_TRY(cudaGetLastError(), "rpool_backward_kernel launch");
         }
         g_launches++;

@@ -67,6 +67,10 @@ struct KParams {
     int force_path;
     int wait_fill;   // backward: this launch started in the zero fill's tail and must wait before it adds
     int staged_slots; // staged backward: schedule slots per CTA (ceil(R / gridDim.x))
+    // tail of a launch in finer pieces: the RoIs at launch places >= tail_start are each served by
+    // tail_parts CTAs (a contiguous share of the tasks each), so that the launch drains in a
+    // fraction of a full CTA's duration.  tail_start = R, tail_parts = 1: one CTA per RoI throughout
+    int tail_start, tail_parts;
 };
 
 // ---------------------------------------------------------------------------

@@ -63,11 +63,28 @@ __device__ __forceinline__ void roi_decode(const KParams &P, int slot, RoiCtx &c
     c.fast_ok = shapes_allow_tables(P, c.L);
 }
 
+// Launch place of this CTA (the RoI's position in launch order) and, in the split tail of the
+// launch, which share of the RoI's tasks it takes.
+__device__ __forceinline__ int launch_place(const KParams &P, int &part)
+{
+    const int b = (int)blockIdx.x;
+    part = 0;
+    if (b < P.tail_start) return b;
+    const int j = b - P.tail_start;
+    part = j % P.tail_parts;
+    return P.tail_start + j / P.tail_parts;
+}
+__device__ __forceinline__ int launch_parts(const KParams &P)
+{
+    return (int)blockIdx.x < P.tail_start ? 1 : P.tail_parts;
+}
 __device__ __forceinline__ int launch_slot(const KParams &P)
 {
     // the backward launch walks the schedule from its far end: coarse levels (the
     // widest windows, the longest CTAs) first, short CTAs in the tail of the launch
-    return P.reverse ? P.R - 1 - (int)blockIdx.x : (int)blockIdx.x;
+    int part;
+    const int place = launch_place(P, part);
+    return P.reverse ? P.R - 1 - place : place;
 }
 
 __device__ __forceinline__ void roi_prologue(const KParams &P, RoiCtx &c)
@@ -92,7 +109,7 @@ __device__ __forceinline__ void load_record(const KParams &P, BlockCtl *ctl)
     // has been pushed out to HBM by the maps streaming through L2 by the time its CTA starts).  Measured
     // on cfg 1: forward 0.1805 -> 0.1777 ms with 74, 0.1785 with 148-296, 0.1789 with 592; backward unchanged
     constexpr int kRecAhead = 74;
-    if (threadIdx.x == 32 && (int)blockIdx.x + kRecAhead < P.R) {
+    if (threadIdx.x == 32 && (int)blockIdx.x + kRecAhead < P.tail_start) {
         const int ahead = (int)blockIdx.x + kRecAhead;
         const int slot = P.reverse ? P.R - 1 - ahead : ahead;
         prefetch_l2_bulk(P.recs + (size_t)slot * P.rec_stride, (unsigned)P.rec_stride);
@@ -331,7 +348,12 @@ __device__ __forceinline__ void fwd_tasks(const KParams &P, const RoiCtx &c, con
 
     int ntask = 0;
     for (int h = 0; h < P.n_heads; ++h) ntask += P.PH[h] * slabs;
-    for (int t = warp; t < ntask; t += nwarps) {
+    // (split tail of the launch: this CTA's share of the tasks, whole bin rows first)
+    int part;
+    launch_place(P, part);
+    const int parts = launch_parts(P);
+    const int t_begin = ntask * part / parts, t_end = ntask * (part + 1) / parts;
+    for (int t = t_begin + warp; t < t_end; t += nwarps) {
         int h = 0, tt = t;
         while (tt >= P.PH[h] * slabs) { tt -= P.PH[h] * slabs; ++h; }
         const int ph = tt / slabs;
@@ -407,7 +429,9 @@ rpool_forward_kernel(const __grid_constant__ KParams P)
     ctx_from_record(P, ctl, c);
     const int need = kRecValid | kRecShape | kRecFits;
     if ((ctl->flags & need) != need || P.force_path == kPathGeneric || !pointers_aligned(P, c.L)) {
-        generic_forward(P);
+        int part;
+        launch_place(P, part);
+        if (part == 0) generic_forward(P);
         return;
     }
     if (P.C == 256) fwd_tasks<256>(P, c, ctl);
@@ -528,8 +552,12 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
     float *img = c.L.data + (size_t)c.b * c.L.H * c.L.W * C;
 
     const int ntask = Hc * slabs;
+    int part;
+    launch_place(P, part);
+    const int parts = launch_parts(P);
+    const int t_begin = ntask * part / parts, t_end = ntask * (part + 1) / parts;
     bool waited = false;
-    for (int t = warp; t < ntask; t += nwarps) {
+    for (int t = t_begin + warp; t < t_end; t += nwarps) {
         const int i = t / slabs;
         const int ch = (t - i * slabs) * 128 + lane * 4;
         const bool active = kExact || ch < C;
@@ -716,8 +744,10 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     const int x0 = ctl->wmin[1], x1 = ctl->wmax[1];
     const int y0 = ctl->wmin[0], y1 = ctl->wmax[0];
     if (!table_ok || y1 - y0 >= kExt) {
+        int part;
+        launch_place(P, part);
         if (P.det) { if (threadIdx.x == 0) atomicExch(P.det_err, 1); }   // no ordered generic path
-        else generic_backward(P, launch_slot(P));
+        else if (part == 0) generic_backward(P, launch_slot(P));
         bwd_release(P);
         return;
     }
@@ -743,12 +773,20 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
         // row-ahead mode, head of the window: the bin rows of window rows [0, lead)
         const int lead = -P.prefetch - 1;
         int row = threadIdx.x;
+        // (a CTA of the split tail starts at its own first window row)
+        int part;
+        launch_place(P, part);
+        const int Hc = y1 - y0 + 1;
+        const int first = (Hc * ((P.C + 127) >> 7) * part / launch_parts(P)) / ((P.C + 127) >> 7);
         for (int h = 0; h < P.n_heads; ++h) {
             if (row >= 0 && row < P.PH[h]) {
-                const int last = (lead < y1 - y0 + 1 ? lead : y1 - y0 + 1) - 1;
-                int hi = 0;
-                for (int i = 0; i <= last; ++i) hi = tt[h].pb[i] > hi ? tt[h].pb[i] : hi;
-                if (row < hi) {
+                const int last = (first + lead < Hc ? first + lead : Hc) - 1;
+                int hi = 0, lo = 0x7fffffff;
+                for (int i = first; i <= last; ++i) {
+                    hi = tt[h].pb[i] > hi ? tt[h].pb[i] : hi;
+                    lo = tt[h].pa[i] < lo ? tt[h].pa[i] : lo;
+                }
+                if (row < hi && row >= lo) {
                     const size_t row_floats = (size_t)P.PW[h] * P.C;
                     prefetch_l2_bulk(P.pooled[h] + ((size_t)c.r * P.PH[h] + row) * row_floats,
                                      (unsigned)(row_floats * 4));
