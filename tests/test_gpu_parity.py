@@ -429,6 +429,28 @@ def test_tensors_on_a_device_that_is_not_current():
         _engine.forward([x.cuda(0) for x in f1], torch.from_numpy(rois).to(d1), None, scales, [7])
 
 
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_split_tail_of_a_launch_longer_than_two_waves(force_generic):
+    """A forward launch of at least two waves serves the RoIs at its last launch places with two
+    CTAs each (a share of the bin rows per CTA; one of them alone on the generic path): every row
+    of both pooled sizes must still be written exactly once, for an odd RoI count too."""
+    rng, feats, rois, levels, scales = make_case(seed=77, C=8, per_img=701)
+    rois = rois[:-1]                       # 1401 RoIs: odd, more than two waves of 128-thread CTAs
+    levels = levels[:-1]
+    gys = [synth.make_gy(rng, rois.shape[0], 8, P) for P in (7, 14)]
+    opts = dict(force_path=_lib.PATH_GENERIC) if force_generic else None
+    outs, grads, plan = run_fused(feats, rois, None, scales, [7, 14], S=2, gys=gys, options=opts)
+    lv, _ = _engine.read_plan(plan)
+    assert np.array_equal(lv, levels)
+    want, wg = oracle_fused(feats, rois, levels, scales, [7, 14], 2, "caffe2", gys)
+    for o, w in zip(outs, want):
+        assert oracle.rel_err(o, w) <= FWD_TOL
+        if force_generic:
+            assert np.array_equal(o, w)    # the generic path is bit-equal to the oracle
+    for g, w in zip(grads, wg):
+        assert oracle.rel_err(g, w) <= BWD_TOL
+
+
 def test_schedule_is_stable_binning_and_rows_keep_input_order():
     rng, feats, rois, levels, scales = make_case(seed=13, C=8, per_img=500)
     for order_mode in (_lib.SCHED_INPUT, _lib.SCHED_DEFAULT, _lib.SCHED_LEVEL_DESC, _lib.SCHED_COARSE_FIRST):
