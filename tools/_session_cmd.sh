@@ -1,13 +1,27 @@
-nvidia-smi -L | wc -l
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 30 --warmup 5 --e2e-steps 5 --no-cpu-baseline --no-gpu-baseline 2>gpurun_out/r03n_n8.err | tail -1 > gpurun_out/r03n_n8.json
-echo "b200 rc=$?"
-python - <<P
+for rep in 1 2 3; do
+for v in base mw1; do
+  if [ $v = base ]; then unset RPOOL_B200_LIB; else export RPOOL_B200_LIB=$PWD/build/exp/$v.so; fi
+  for c in 0; do
+  python bench.py --config $c --steps 100 --warmup 10 --no-e2e --no-cpu-baseline --no-gpu-baseline > gpurun_out/r03o_$v$c.json 2> gpurun_out/r03o_$v$c.err
+  python - <<P
 import json
-d=json.loads(open("gpurun_out/r03n_n8.json").read())
-r=d["roofline"]; e=d.get("e2e") or {}; s=d.get("strong") or {}
-print("n8 weak: %.4g RoIs/s %.4f ms frac %.3f" % (d["value"], d["ms_per_step"], (r.get("fwd_plus_bwd") or {}).get("frac", 0)))
-print("e2e: %.3g RoIs/s %.1f ms probe %.1f ms bound %s" % (e.get("value", 0), e.get("ms_per_step", 0), (e.get("copy_only_probe") or {}).get("ms_per_step", 0), e.get("bound")))
-print("strong: %.4f ms n1 %.4f eff %.3f ok %s frac %.3f" % (s.get("ms_per_step", 0), s.get("n1_ms_per_step", 0), s.get("efficiency_vs_n1", 0), (s.get("sharded_equals_unsharded") or {}).get("ok"), (s.get("roofline") or {}).get("frac", 0)))
+try:
+    d=json.loads(open("gpurun_out/r03o_$v$c.json").read().strip().splitlines()[-1])
+    r=d["roofline"]
+    print("$v cfg$c step %.4f ms | from python %.4f (fwd %.4f bwd %.4f) parity %s" % (
+        d["ms_per_step"], r["launched_from_python"]["ms_per_step"],
+        r["launched_from_python"]["fwd_ms"], r["launched_from_python"]["bwd_ms"], d["parity"]["ok"]))
+except Exception as e:
+    print("$v FAILED", e); print(open("gpurun_out/r03o_$v$c.err").read()[-800:])
 P
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29523 bench.py --impl reference --gpus 8 --steps 3 --warmup 1 2>gpurun_out/r03n_ref_n8.err | tail -1 > gpurun_out/r03n_ref_n8.json
-cut -c1-300 gpurun_out/r03n_ref_n8.json
+  done
+done
+done
+unset RPOOL_B200_LIB
+ncu --metrics gpu__time_duration.sum --clock-control none -c 12 --csv --log-file gpurun_out/r03o_cfg0_launches.csv python bench.py --config 0 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-gpu-baseline --no-parity --no-graph > /dev/null 2>&1
+python - <<P
+import csv
+rows=list(csv.reader(l for l in open('gpurun_out/r03o_cfg0_launches.csv') if l.startswith('"')))
+h=rows[0]; ki=h.index("Kernel Name"); vi=h.index("Metric Value")
+print([(r[ki].split('(')[0].replace('rpool::rpool_','')[:20], float(r[vi])/1000) for r in rows[1:]])
+P
