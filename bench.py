@@ -813,7 +813,9 @@ def run_b200(args):
                           "ncu --set full, per launch)",
         "peak_source": peak_src,
         "ncu": ncu_view(args.config, S),
-        "kernel": ("rpool_backward_kernel" + ("" if forked else " + rpool_zero_kernel")
+        "kernel": (("rpool_det_scan_kernel + rpool_backward_det_window_kernel + rpool_det_gather_kernel"
+                    if args.deterministic else
+                    "rpool_backward_kernel" + ("" if forked else " + rpool_zero_kernel"))
                    if dom == "backward"
                    else "rpool_plan_kernel + rpool_forward_kernel"),
         "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms,

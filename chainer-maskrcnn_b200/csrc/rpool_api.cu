@@ -308,7 +308,7 @@ int staged_grid(const rpool_problem *q, const Options &o, int &smem)
 // and only ever needs to grow, so the largest value set so far is remembered per
 // (kernel, device) and the driver call is skipped when it already covers `smem`.
 constexpr int kSmemCacheDevices = 64;
-std::atomic<int> g_smem_set[3][kSmemCacheDevices];
+std::atomic<int> g_smem_set[4][kSmemCacheDevices];
 
 template <typename Kern>
 int set_smem(Kern kern, int which, int smem)
@@ -329,10 +329,6 @@ int set_smem(Kern kern, int which, int smem)
 // Split tail of a pooling launch (KParams::tail_start / tail_parts): the last resident-CTAs' worth of
 // work is handed out in `parts` pieces per RoI, so that the launch drains in 1 / parts of a full CTA's
 // duration.  Only for launches of more than two waves; returns the grid size.
-// Measured (profiles/r02_experiments.log, r03j..l): two pieces per RoI in the forward launch's tail take
-// 2.4 % off the forward of configs[1] and 5.3 % off a 2 000-RoI shard of configs[3]; three or four pieces
-// are no better; the backward launch, which already ends on its shortest CTAs, does not gain.
-constexpr int kTailPartsFwd = 2, kTailPartsBwd = 1;
 template <typename Kern>
 int split_tail(Kern kern, int threads, int smem, int parts, KParams &k)
 {
@@ -615,11 +611,11 @@ static int backward_det(const rpool_problem *p, void *ws, const Options &o, cuda
         k.det = 1;
         k.det_scratch = static_cast<float *>(p->det_workspace);
         k.det_scratch_floats = p->det_workspace_bytes / sizeof(float);
-        rc = set_smem(rpool_backward_kernel, 1, smem);
+        rc = set_smem(rpool_backward_det_window_kernel, 3, smem);
         if (rc) return rc;
         // in the scan kernel's tail (waits before it reads the offsets)
-        CUDA_TRY(launch_in_tail(rpool_backward_kernel, dim3(p->n_rois), dim3(threads), (size_t)smem, st, k),
-                 "rpool_backward_kernel launch");
+        CUDA_TRY(launch_in_tail(rpool_backward_det_window_kernel, dim3(p->n_rois), dim3(threads), (size_t)smem, st, k),
+                 "rpool_backward_det_window_kernel launch");
         g_launches++;
     }
     GatherParams g;

@@ -63,6 +63,13 @@ __device__ __forceinline__ void roi_decode(const KParams &P, int slot, RoiCtx &c
     c.fast_ok = shapes_allow_tables(P, c.L);
 }
 
+// Pieces per RoI in the tail of a launch (see split_tail in rpool_api.cu).  Measured
+// (profiles/r02_experiments.log, r03j..l): two pieces per RoI in the forward launch's tail take 2.4 % off
+// the forward of configs[1] and 5.3 % off a 2 000-RoI shard of configs[3]; three or four are no better;
+// the backward launch, which already ends on its shortest CTAs, does not gain -- and with 1 here the
+// backward kernel carries none of the bookkeeping.
+constexpr int kTailPartsFwd = 2, kTailPartsBwd = 1;
+
 // Launch place of this CTA (the RoI's position in launch order) and, in the split tail of the
 // launch, which share of the RoI's tasks it takes.
 __device__ __forceinline__ int launch_place(const KParams &P, int &part)
@@ -539,7 +546,10 @@ __device__ __forceinline__ void bwd_col_pass(float4 (&G)[kSW], unsigned long lon
 
 // kC as in the forward kernel; kExact: PW is a multiple of kZ and C of 128, so
 // no lane and no chunk position is ever masked.
-template <int kC, bool kExact>
+// kDet: the deterministic variant's window pass (each RoI's contribution goes to its private window
+// with plain stores).  A compile-time switch and a kernel of its own, so that the bookkeeping of the
+// first-touch stores costs the atomic kernel no registers.
+template <int kC, bool kExact, bool kDet>
 __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, const BlockCtl *ctl,
                                           const TTab *tt, uint32_t strip, float *det_win)
 {
@@ -552,10 +562,14 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
     float *img = c.L.data + (size_t)c.b * c.L.H * c.L.W * C;
 
     const int ntask = Hc * slabs;
-    int part;
-    launch_place(P, part);
-    const int parts = launch_parts(P);
-    const int t_begin = ntask * part / parts, t_end = ntask * (part + 1) / parts;
+    int t_begin = 0, t_end = ntask;
+    if (kTailPartsBwd > 1) {
+        int part;
+        launch_place(P, part);
+        const int parts = launch_parts(P);
+        t_begin = ntask * part / parts;
+        t_end = ntask * (part + 1) / parts;
+    }
     bool waited = false;
     for (int t = t_begin + warp; t < t_end; t += nwarps) {
         const int i = t / slabs;
@@ -655,7 +669,7 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
                 else if (NX == 3) bwd_col_pass<3>(G, cnt, wp, zp);
                 else bwd_col_pass<4>(G, cnt, wp, zp);
                 const unsigned m = ctl->hd[h].cmask[q];
-                if (det_win == nullptr) {
+                if (!kDet) {
                     // (launched early, in the zero fill's tail: everything up to here only read gy
                     // and the plan; the gradients must be clean before the first reduction)
                     if (P.wait_fill && !waited) { bwd_release(P); waited = true; }
@@ -688,7 +702,7 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
             }
             __syncwarp();
         }
-        if (det_win != nullptr && det_wc <= 64 && active) {
+        if (kDet && det_wc <= 64 && active) {
             // deterministic: the cells of this window row that received nothing
             float *gp = det_win + (size_t)i * det_wc * C + ch;
             for (int col = 0; col < det_wc; ++col)
@@ -697,15 +711,15 @@ __device__ __forceinline__ void bwd_tasks(const KParams &P, const RoiCtx &c, con
     }
 }
 
-__global__ void __launch_bounds__(kMaxThreads, RPOOL_MIN_BLOCKS)
-rpool_backward_kernel(const __grid_constant__ KParams P)
+template <bool kDet>
+__device__ __forceinline__ void backward_body(const KParams &P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockCtl *ctl = reinterpret_cast<BlockCtl *>(smem_raw);
     // The launch for the next pooled size may use this one's tail.  It does not wait for anything
     // itself, so when THIS launch started early (in the zero fill's tail, wait_fill) a CTA gives
     // the signal only once it has seen the fill complete -- see bwd_release.
-    if (!P.wait_fill && !P.det) allow_dependents_early();
+    if (!P.wait_fill && !kDet) allow_dependents_early();
     const int kCtlBytes = (rec_bytes(P.n_heads) + 127) & ~127;   // only this launch's head parts are loaded
     constexpr int kTTabBytes = (sizeof(TTab) + 127) & ~127;
     TTab *tt = reinterpret_cast<TTab *>(smem_raw + kCtlBytes);
@@ -729,7 +743,7 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     }
 
     load_record(P, ctl);
-    if (P.det) {
+    if (kDet) {
         // launched in the scan kernel's tail: its offsets from here on.  The gather launch queued behind
         // this one lists its windows (rectangles: the scan's output) as soon as every CTA has got here.
         wait_for_predecessors();
@@ -744,16 +758,16 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
     const int x0 = ctl->wmin[1], x1 = ctl->wmax[1];
     const int y0 = ctl->wmin[0], y1 = ctl->wmax[0];
     if (!table_ok || y1 - y0 >= kExt) {
-        int part;
-        launch_place(P, part);
-        if (P.det) { if (threadIdx.x == 0) atomicExch(P.det_err, 1); }   // no ordered generic path
+        int part = 0;
+        if (kTailPartsBwd > 1) launch_place(P, part);
+        if (kDet) { if (threadIdx.x == 0) atomicExch(P.det_err, 1); }   // no ordered generic path
         else if (part == 0) generic_backward(P, launch_slot(P));
         bwd_release(P);
         return;
     }
     if (x1 < x0 || y1 < y0) { bwd_release(P); return; }
     float *det_win = nullptr;
-    if (P.det) {
+    if (kDet) {
         // this RoI's private window in the scratch buffer: zero it, then the tasks
         // below add into it with plain stores
         const int *rc = P.det_rects + 4 * (size_t)launch_slot(P);
@@ -774,10 +788,13 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
         const int lead = -P.prefetch - 1;
         int row = threadIdx.x;
         // (a CTA of the split tail starts at its own first window row)
-        int part;
-        launch_place(P, part);
         const int Hc = y1 - y0 + 1;
-        const int first = (Hc * ((P.C + 127) >> 7) * part / launch_parts(P)) / ((P.C + 127) >> 7);
+        int first = 0;
+        if (kTailPartsBwd > 1) {
+            int part;
+            launch_place(P, part);
+            first = (Hc * ((P.C + 127) >> 7) * part / launch_parts(P)) / ((P.C + 127) >> 7);
+        }
         for (int h = 0; h < P.n_heads; ++h) {
             if (row >= 0 && row < P.PH[h]) {
                 const int last = (first + lead < Hc ? first + lead : Hc) - 1;
@@ -801,9 +818,22 @@ rpool_backward_kernel(const __grid_constant__ KParams P)
                            (uint32_t)warp * (uint32_t)P.strip_cols * 512u + (uint32_t)lane * 16u;
     bool exact = (P.C == 256);
     for (int h = 0; h < P.n_heads; ++h) exact = exact && (P.PW[h] % kZ == 0);
-    if (exact) bwd_tasks<256, true>(P, c, ctl, tt, strip, det_win);
-    else bwd_tasks<0, false>(P, c, ctl, tt, strip, det_win);
+    if (exact) bwd_tasks<256, true, kDet>(P, c, ctl, tt, strip, det_win);
+    else bwd_tasks<0, false, kDet>(P, c, ctl, tt, strip, det_win);
     bwd_release(P);
+}
+
+__global__ void __launch_bounds__(kMaxThreads, RPOOL_MIN_BLOCKS)
+rpool_backward_kernel(const __grid_constant__ KParams P)
+{
+    backward_body<false>(P);
+}
+
+// the deterministic variant's window pass (KParams::det = 1)
+__global__ void __launch_bounds__(kMaxThreads, RPOOL_MIN_BLOCKS)
+rpool_backward_det_window_kernel(const __grid_constant__ KParams P)
+{
+    backward_body<true>(P);
 }
 
 // ---------------------------------------------------------------------------
