@@ -1,8 +1,9 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 2 --steps 20 --warmup 3 --no-e2e --no-cpu-baseline --no-gpu-baseline --no-parity 2>gpurun_out/r03t_n2.err | tail -1 > gpurun_out/r03t_n2.json
+# what the driver runs at round end, on the committed tree: smoke(), then the default bench line
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python bench.py > gpurun_out/r03u_bench_default.json 2> gpurun_out/r03u_bench_default.err
 python - <<P
 import json
-d=json.loads(open("gpurun_out/r03t_n2.json").read())
-s=d["strong"]
-print(d["n_gpus"], "%.4g"%d["value"], d["ms_per_step"], {k:s.get(k) for k in ("ms_per_step","n1_ms_per_step","efficiency_vs_n1","ms_per_step_repeats","n1_ms_per_step_repeats")}, s["sharded_equals_unsharded"]["ok"])
+d=json.loads(open("gpurun_out/r03u_bench_default.json").read().strip().splitlines()[-1])
+r=d["roofline"]
+print(d["metric"], "%.4g"%d["value"], d["unit"], "steps", d["steps"], "ms/step %.4f"%d["ms_per_step"], "pair frac %.3f step frac %.3f"%(r["frac"], r["fwd_plus_bwd"]["frac"]), "e2e %.4g"%d["e2e"]["value"], "cpu %.4g x%d"%(d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"]), "launches", d["gpu_launches"], "parity", d["parity"]["ok"], d["clocks"]["reasons"], d["how"]["build_id"])
 P
-tail -3 gpurun_out/r03t_n2.err
